@@ -1,0 +1,48 @@
+"""ctypes loader for the C-ABI library.  The product path has NO fallback: if libheal_b200.so is
+missing or fails to load, importing this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libheal_b200.so")
+
+_c = ctypes
+_vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/heal_b200.h declares
+SIGNATURES = {
+    "heal_abi_version": (_i, []),
+    "heal_device_check": (_i, []),
+    "heal_voxelize_workspace": (_sz, [_i, _i, _i]),
+    "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "heal_conv2d_nhwc_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i,
+                                  _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "heal_pyramid_fuse_level": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "heal_att_fuse": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+}
+
+ERRORS = {-1: "HEAL_ERR_ARG", -2: "HEAL_ERR_WORKSPACE", -3: "HEAL_ERR_LAUNCH", -4: "HEAL_ERR_UNSUPPORTED",
+          -5: "HEAL_ERR_DRIVER"}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m heal_b200.build` (nvcc, sm_100a). "
+            "heal_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"{what} failed: {ERRORS.get(code, code)}")

@@ -1,0 +1,243 @@
+// Multi-agent BEV feature fusion kernels (channels-last):
+//   heal_pyramid_fuse_level : warp(feat) + warp(score) -> mask -> softmax over agents -> weighted sum
+//       reference: opencood/models/fuse_modules/pyramid_fuse.py:17-63 (weighted_fuse) and :143-164
+//       (score = sigmoid(occ) + 1e-4, camera crop mask in eval mode)
+//   heal_att_fuse           : warp -> per-pixel scaled dot-product attention over agents, ego row only
+//       reference: opencood/models/fuse_modules/fusion_in_one.py:126-151 (AttFusion), :41-45
+// Both fold warp_affine_simple (torch_transformation_utils.py:323-332 = F.affine_grid with an fp64
+// theta, cast to fp32, then F.grid_sample bilinear / zeros padding) into the fusion so the warped
+// per-agent maps never exist in HBM.
+#include "common.cuh"
+#include "../../include/heal_b200.h"
+
+namespace {
+
+constexpr int MAX_AGENTS = 8;
+
+struct Tap {
+    int off[4];    // source pixel index (within the agent's map) or -1 when out of bounds
+    float w[4];    // bilinear weights (nw, ne, sw, se)
+};
+
+// affine_grid (fp64, then cast to fp32) + grid_sample unnormalisation; pytorch semantics.
+__device__ __forceinline__ Tap make_tap(const double* __restrict__ th, int oh, int ow, int H, int W, int align) {
+    double xb, yb;
+    if (align) {
+        xb = (W > 1) ? (-1.0 + 2.0 * ow / (double)(W - 1)) : 0.0;
+        yb = (H > 1) ? (-1.0 + 2.0 * oh / (double)(H - 1)) : 0.0;
+    } else {
+        xb = (2.0 * ow + 1.0) / (double)W - 1.0;
+        yb = (2.0 * oh + 1.0) / (double)H - 1.0;
+    }
+    float gx = (float)(th[0] * xb + th[1] * yb + th[2]);
+    float gy = (float)(th[3] * xb + th[4] * yb + th[5]);
+    float ix, iy;
+    if (align) { ix = ((gx + 1.f) / 2.f) * (float)(W - 1); iy = ((gy + 1.f) / 2.f) * (float)(H - 1); }
+    else { ix = ((gx + 1.f) * (float)W - 1.f) / 2.f; iy = ((gy + 1.f) * (float)H - 1.f) / 2.f; }
+    float fx = floorf(ix), fy = floorf(iy);
+    // clamp before the int cast so that huge/NaN coordinates become plainly out of bounds
+    int x0 = (fx >= -2.f && fx <= (float)(W + 1)) ? (int)fx : -2;
+    int y0 = (fy >= -2.f && fy <= (float)(H + 1)) ? (int)fy : -2;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+    Tap t;
+    bool xi0 = (x0 >= 0 && x0 < W), xi1 = (x1 >= 0 && x1 < W), yi0 = (y0 >= 0 && y0 < H), yi1 = (y1 >= 0 && y1 < H);
+    t.off[0] = (xi0 && yi0) ? y0 * W + x0 : -1;  t.w[0] = wx0 * wy0;   // nw
+    t.off[1] = (xi1 && yi0) ? y0 * W + x1 : -1;  t.w[1] = wx1 * wy0;   // ne
+    t.off[2] = (xi0 && yi1) ? y1 * W + x0 : -1;  t.w[2] = wx0 * wy1;   // sw
+    t.off[3] = (xi1 && yi1) ? y1 * W + x1 : -1;  t.w[3] = wx1 * wy1;   // se
+    return t;
+}
+
+struct FuseP {
+    const float* feat;     // (n, H, W, C) channels-last, pixel stride cs
+    const float* occ;      // (n, H, W) occupancy logits
+    const double* theta;   // (n, 2, 3) fp64: affine[b, 0, j]
+    const int* crop;       // (n, 4) [h0, h1, w0, w1] window where the score is kept, or nullptr
+    float* out;            // (H, W, C) pixel stride out_cs, channel offset out_co
+    int n, H, W, C, cs, out_cs, out_co, align;
+};
+
+constexpr int FUSE_PIX = 32;
+
+__global__ void __launch_bounds__(256)
+k_pyramid_fuse(FuseP p) {
+    __shared__ Tap sTap[FUSE_PIX][MAX_AGENTS];
+    __shared__ float sScore[FUSE_PIX][MAX_AGENTS];
+    const int HW = p.H * p.W;
+    const int pix0 = blockIdx.x * FUSE_PIX;
+    // phase 1: tap geometry + warped score per (pixel, agent)
+    for (int it = threadIdx.x; it < FUSE_PIX * p.n; it += blockDim.x) {
+        int j = it % p.n, lp = it / p.n;
+        int pix = pix0 + lp;
+        if (pix >= HW) continue;
+        Tap t = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
+        const float* occ = p.occ + (size_t)j * HW;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (t.off[k] >= 0) {
+                float sc = 1.f / (1.f + expf(-occ[t.off[k]])) + 1e-4f;
+                if (p.crop) {
+                    int y = t.off[k] / p.W, x = t.off[k] % p.W;
+                    const int* c = p.crop + 4 * j;
+                    if (!(y >= c[0] && y < c[1] && x >= c[2] && x < c[3])) sc = 0.f;
+                }
+                s += sc * t.w[k];
+            }
+        }
+        sTap[lp][j] = t;
+        sScore[lp][j] = s;
+    }
+    __syncthreads();
+    // phase 2: masked softmax over agents (score == 0 -> -inf; all -inf -> NaN -> 0), folded into tap weights
+    if (threadIdx.x < FUSE_PIX && pix0 + threadIdx.x < HW) {
+        int lp = threadIdx.x;
+        float mx = -INFINITY;
+        for (int j = 0; j < p.n; ++j) { float s = sScore[lp][j]; if (s != 0.f) mx = fmaxf(mx, s); }
+        float den = 0.f;
+        float e[MAX_AGENTS];
+        for (int j = 0; j < p.n; ++j) {
+            float s = sScore[lp][j];
+            e[j] = (s != 0.f) ? expf(s - mx) : 0.f;
+            den += e[j];
+        }
+        for (int j = 0; j < p.n; ++j) {
+            float wgt = (den > 0.f) ? e[j] / den : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sTap[lp][j].w[k] *= wgt;
+        }
+    }
+    __syncthreads();
+    // phase 3: thread = (pixel, 4-channel chunk)
+    const int chunks = p.C / 4;
+    for (int it = threadIdx.x; it < FUSE_PIX * chunks; it += blockDim.x) {
+        int ch = it % chunks, lp = it / chunks;
+        int pix = pix0 + lp;
+        if (pix >= HW) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < p.n; ++j) {
+            const float* fj = p.feat + (size_t)j * HW * p.cs + ch * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);   // warped feature (bilinear), then weighted
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int off = sTap[lp][j].off[k];
+                if (off >= 0) {
+                    float w = sTap[lp][j].w[k];
+                    float4 v = ldg_f4(fj + (size_t)off * p.cs);
+                    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+                }
+            }
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        stg_f4(p.out + (size_t)pix * p.out_cs + p.out_co + ch * 4, acc);
+    }
+}
+
+struct AttP {
+    const float* feat; const double* theta; float* out;
+    int n, H, W, C, cs, out_cs, out_co, align;
+    float inv_sqrt_dim;
+};
+
+// one warp per output pixel; lane covers channels {4*lane + 128*q}
+template <int Q>
+__global__ void __launch_bounds__(256)
+k_att_fuse(AttP p) {
+    const int HW = p.H * p.W;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pix = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (pix >= HW) return;
+    Tap taps[MAX_AGENTS];
+    for (int j = 0; j < p.n; ++j) taps[j] = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
+    auto sample = [&](int j, float4* x) {
+        const float* fj = p.feat + (size_t)j * HW * p.cs + 4 * lane;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int off = taps[j].off[k];
+            if (off >= 0) {
+                float w = taps[j].w[k];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    float4 v = ldg_f4(fj + (size_t)off * p.cs + 128 * q);
+                    x[q].x = fmaf(v.x, w, x[q].x); x[q].y = fmaf(v.y, w, x[q].y);
+                    x[q].z = fmaf(v.z, w, x[q].z); x[q].w = fmaf(v.w, w, x[q].w);
+                }
+            }
+        }
+    };
+    float4 x0[Q], xj[Q];
+    sample(0, x0);
+    float sc[MAX_AGENTS];
+    float mx = -INFINITY;
+    for (int j = 0; j < p.n; ++j) {
+        if (j == 0) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) xj[q] = x0[q];
+        } else sample(j, xj);
+        float d = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) d += x0[q].x * xj[q].x + x0[q].y * xj[q].y + x0[q].z * xj[q].z + x0[q].w * xj[q].w;
+        d = warp_sum(d) * p.inv_sqrt_dim;
+        sc[j] = d;
+        mx = fmaxf(mx, d);
+    }
+    float den = 0.f;
+    for (int j = 0; j < p.n; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+    float4 acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < p.n; ++j) {
+        float a = sc[j] / den;
+        if (j == 0) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) xj[q] = x0[q];
+        } else sample(j, xj);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            acc[q].x = fmaf(a, xj[q].x, acc[q].x); acc[q].y = fmaf(a, xj[q].y, acc[q].y);
+            acc[q].z = fmaf(a, xj[q].z, acc[q].z); acc[q].w = fmaf(a, xj[q].w, acc[q].w);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) stg_f4(p.out + (size_t)pix * p.out_cs + p.out_co + 4 * lane + 128 * q, acc[q]);
+}
+
+}  // namespace
+
+extern "C" int heal_pyramid_fuse_level(const float* feat, int feat_cstride, const float* occ, const double* theta,
+                                       const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
+                                       float* out, int out_cstride, int out_coffset, void* stream_) {
+    if (!feat || !occ || !theta || !out) return HEAL_ERR_ARG;
+    if (n_agents < 1 || n_agents > MAX_AGENTS) return HEAL_ERR_UNSUPPORTED;
+    if ((C & 3) || (feat_cstride & 3) || (out_cstride & 3) || (out_coffset & 3)) return HEAL_ERR_UNSUPPORTED;
+    FuseP p;
+    p.feat = feat; p.occ = occ; p.theta = theta; p.crop = crop_windows; p.out = out;
+    p.n = n_agents; p.H = H; p.W = W; p.C = C; p.cs = feat_cstride; p.out_cs = out_cstride; p.out_co = out_coffset;
+    p.align = align_corners;
+    int grid = (H * W + FUSE_PIX - 1) / FUSE_PIX;
+    k_pyramid_fuse<<<grid, 256, 0, (cudaStream_t)stream_>>>(p);
+    return heal_check_launch();
+}
+
+extern "C" int heal_att_fuse(const float* feat, int feat_cstride, const double* theta, int n_agents, int H, int W, int C,
+                             float* out, int out_cstride, int out_coffset, void* stream_) {
+    if (!feat || !theta || !out) return HEAL_ERR_ARG;
+    if (n_agents < 1 || n_agents > MAX_AGENTS) return HEAL_ERR_UNSUPPORTED;
+    if ((C % 128) || C > 512 || (feat_cstride & 3) || (out_cstride & 3) || (out_coffset & 3)) return HEAL_ERR_UNSUPPORTED;
+    AttP p;
+    p.feat = feat; p.theta = theta; p.out = out; p.n = n_agents; p.H = H; p.W = W; p.C = C; p.cs = feat_cstride;
+    p.out_cs = out_cstride; p.out_co = out_coffset; p.align = 0;
+    p.inv_sqrt_dim = 1.0f / sqrtf((float)C);
+    int grid = (H * W + 7) / 8;
+    cudaStream_t st = (cudaStream_t)stream_;
+    switch (C / 128) {
+        case 1: k_att_fuse<1><<<grid, 256, 0, st>>>(p); break;
+        case 2: k_att_fuse<2><<<grid, 256, 0, st>>>(p); break;
+        case 3: k_att_fuse<3><<<grid, 256, 0, st>>>(p); break;
+        default: k_att_fuse<4><<<grid, 256, 0, st>>>(p); break;
+    }
+    return heal_check_launch();
+}

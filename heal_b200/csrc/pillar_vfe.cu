@@ -1,0 +1,101 @@
+// Fused PillarVFE (10-d point augmentation -> Linear(10,64) -> BatchNorm1d(eval) -> ReLU -> max over the
+// T slots) + PointPillarScatter into a channels-last BEV canvas.
+// Reference: opencood/models/sub_modules/pillar_vfe.py:105-155 (PillarVFE.forward), :31-53 (PFNLayer),
+//            opencood/models/sub_modules/point_pillar_scatter.py:19-77.
+// One warp per pillar. Stage A: lane = point slot (coalesced 16 B loads, warp-reduced mean).
+// Stage B: lane = channel pair, point features broadcast from shared memory, running max in
+// registers, one coalesced 256 B store of the pillar's 64 channels into canvas[b][y][x][:].
+// Parity traps kept: padded slots are zeroed BEFORE the linear layer and therefore contribute
+// ReLU(BN(0)) to the max (pillar_vfe.py:149,46); scatter index = z + y*nx + x (scatter.py:58).
+#include "common.cuh"
+#include "../../include/heal_b200.h"
+
+namespace {
+
+constexpr int PV_WARPS = 8;
+constexpr int PV_COUT = 64;
+constexpr int PV_CIN = 10;
+
+struct PvCfg {
+    float vx, vy, vz;
+    float xoff, yoff, zoff;
+    int T, nx, ny;
+};
+
+__global__ void __launch_bounds__(PV_WARPS * 32)
+k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ num_points,
+                     const int4* __restrict__ coords, const int* __restrict__ num_voxels_dev, int M,
+                     const float* __restrict__ Wf, const float* __restrict__ bf, PvCfg c,
+                     float* __restrict__ pillar_out, float* __restrict__ canvas) {
+    __shared__ float sW[PV_CIN * PV_COUT];
+    __shared__ float sB[PV_COUT];
+    __shared__ __align__(16) float sF[PV_WARPS][32][12];
+    for (int i = threadIdx.x; i < PV_CIN * PV_COUT; i += blockDim.x) sW[i] = Wf[i];
+    if (threadIdx.x < PV_COUT) sB[threadIdx.x] = bf[threadIdx.x];
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int v = blockIdx.x * PV_WARPS + warp;
+    int Mdev = num_voxels_dev ? min(M, num_voxels_dev[0]) : M;
+    if (v >= Mdev) return;
+
+    // ---- stage A: lane = point slot --------------------------------------------------------
+    int n = num_points[v];
+    int4 cd = coords[v];  // [b, z, y, x]
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < c.T) p = __ldg(voxels + (size_t)v * c.T + lane);
+    float fn = (float)n;
+    float mx = __fdiv_rn(warp_sum(p.x), fn), my = __fdiv_rn(warp_sum(p.y), fn), mz = __fdiv_rn(warp_sum(p.z), fn);
+    float cx = __fadd_rn(__fmul_rn((float)cd.w, c.vx), c.xoff);
+    float cy = __fadd_rn(__fmul_rn((float)cd.z, c.vy), c.yoff);
+    float cz = __fadd_rn(__fmul_rn((float)cd.y, c.vz), c.zoff);
+    float msk = (lane < n) ? 1.f : 0.f;
+    float* f = sF[warp][lane];
+    reinterpret_cast<float4*>(f)[0] = make_float4(p.x * msk, p.y * msk, p.z * msk, p.w * msk);
+    reinterpret_cast<float4*>(f)[1] = make_float4((p.x - mx) * msk, (p.y - my) * msk, (p.z - mz) * msk, (p.x - cx) * msk);
+    reinterpret_cast<float4*>(f)[2] = make_float4((p.y - cy) * msk, (p.z - cz) * msk, 0.f, 0.f);
+    __syncwarp();
+
+    // ---- stage B: lane = channel pair ------------------------------------------------------
+    float w0[PV_CIN], w1[PV_CIN];
+#pragma unroll
+    for (int k = 0; k < PV_CIN; ++k) { w0[k] = sW[k * PV_COUT + 2 * lane]; w1[k] = sW[k * PV_COUT + 2 * lane + 1]; }
+    float b0 = sB[2 * lane], b1 = sB[2 * lane + 1];
+    float m0 = 0.f, m1 = 0.f;  // ReLU output >= 0, so 0 is the identity of the running max
+    for (int t = 0; t < c.T; ++t) {
+        const float4* ft = reinterpret_cast<const float4*>(sF[warp][t]);
+        float4 a = ft[0], b = ft[1], d = ft[2];
+        float x[PV_CIN] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y};
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < PV_CIN; ++k) { y0 = fmaf(x[k], w0[k], y0); y1 = fmaf(x[k], w1[k], y1); }
+        m0 = fmaxf(m0, y0 + b0);
+        m1 = fmaxf(m1, y1 + b1);
+    }
+    float2 o = make_float2(m0, m1);
+    if (pillar_out) reinterpret_cast<float2*>(pillar_out + (size_t)v * PV_COUT)[lane] = o;
+    if (canvas) {
+        size_t cell = ((size_t)cd.x * c.ny + (size_t)cd.z) * c.nx + (size_t)(cd.y + cd.w);  // z + y*nx + x, z == 0
+        reinterpret_cast<float2*>(canvas + cell * PV_COUT)[lane] = o;
+    }
+}
+
+}  // namespace
+
+extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_points, const int* voxel_coords,
+                                       const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
+                                       const float* w_folded, const float* b_folded, int c_in, int c_out,
+                                       const float* voxel_size3, const float* offset3, int nx, int ny,
+                                       float* pillar_features_out, float* canvas_nhwc_out, void* stream_) {
+    if (!voxel_features || !voxel_num_points || !voxel_coords || !w_folded || !b_folded) return HEAL_ERR_ARG;
+    if (c_in != PV_CIN || c_out != PV_COUT || max_points_per_voxel < 1 || max_points_per_voxel > 32) return HEAL_ERR_UNSUPPORTED;
+    if (num_voxels <= 0) return HEAL_OK;
+    PvCfg c;
+    c.vx = voxel_size3[0]; c.vy = voxel_size3[1]; c.vz = voxel_size3[2];
+    c.xoff = offset3[0]; c.yoff = offset3[1]; c.zoff = offset3[2];
+    c.T = max_points_per_voxel; c.nx = nx; c.ny = ny;
+    int grid = (num_voxels + PV_WARPS - 1) / PV_WARPS;
+    k_pillar_vfe_scatter<<<grid, PV_WARPS * 32, 0, (cudaStream_t)stream_>>>(
+        (const float4*)voxel_features, voxel_num_points, (const int4*)voxel_coords, num_voxels_dev, num_voxels,
+        w_folded, b_folded, c, pillar_features_out, canvas_nhwc_out);
+    return heal_check_launch();
+}

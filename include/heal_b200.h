@@ -1,0 +1,101 @@
+/* heal_b200 — C ABI of the B200-native (sm_100a) per-frame perception hot path of HEAL / OpenCOOD.
+ *
+ * The reference (yifanlu0227/HEAL) is pure Python/PyTorch on this path and has NO foreign-function
+ * interface of its own; each entry point below therefore cites the reference *Python* call site it
+ * replaces (path:line relative to the reference root). INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *    or the comment says "host".
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, never
+ *    synchronises, never allocates (callers pass workspaces; heal_*_workspace() gives the size).
+ *  - return value: 0 on success, negative HEAL_ERR_* otherwise (no exceptions cross the ABI).
+ *  - activations are channels-last: a (N,C,H,W) map is stored as [n][h][w][c]; `cstride` is the
+ *    distance in floats between two pixels and `coffset` the first channel used, so that a conv can
+ *    read / write a channel slice of a wider concat buffer.
+ */
+#ifndef HEAL_B200_H_
+#define HEAL_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEAL_B200_ABI_VERSION 1
+int heal_abi_version(void);
+/* sm_100a build check: returns 0 when a Blackwell (cc 10.x) device is current, negative otherwise. */
+int heal_device_check(void);
+
+/* ---- voxelization -------------------------------------------------------------------------
+ * replaces SpVoxelPreprocessor.preprocess + collate_batch for all agents of a scene
+ * (opencood/data_utils/pre_processor/sp_voxel_preprocessor.py:62-85, :145-174 -> spconv CPU
+ * VoxelGeneratorV2.generate / Point2VoxelCPU3d.point_to_voxel). Bit-exact: voxel order = order of
+ * first appearance, first `max_points_per_voxel` points in input order, cells beyond `max_voxels`
+ * dropped, coords = [agent, z, y, x].
+ *   points          (P_total,4) f32, agents concatenated
+ *   agent_offsets   (A+1) i32 device: points of agent a are [off[a], off[a+1])
+ *   range_min3/voxel_size3/grid3   HOST arrays (x,y,z)
+ *   capacity        rows available in the outputs (>= number of voxels produced)
+ *   voxels_out      (capacity,T,4) f32   coords_out (capacity,4) i32   num_points_out (capacity) i32
+ *   num_voxels_out  (1+A) i32: [0] = M total, [1+a] = voxels of agent a */
+size_t heal_voxelize_workspace(int num_points_total, int capacity, int num_agents);
+int heal_voxelize(const float* points, const int* agent_offsets, int num_agents, int num_points_total,
+                  const float* range_min3_host, const float* voxel_size3_host, const int* grid3_host,
+                  int max_points_per_voxel, int max_voxels, int capacity,
+                  float* voxels_out, int* coords_out, int* num_points_out, int* num_voxels_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* MeanVFE.forward (opencood/models/sub_modules/mean_vfe.py:13-33): (M,T,4) -> (M,4) */
+int heal_mean_vfe(const float* voxels, const int* num_points, int num_voxels, int max_points_per_voxel,
+                  float* mean_out, void* stream);
+
+/* ---- PillarVFE + PointPillarScatter, fused --------------------------------------------------
+ * replaces PillarVFE.forward (opencood/models/sub_modules/pillar_vfe.py:105-155, PFNLayer :31-53)
+ * and PointPillarScatter.forward (opencood/models/sub_modules/point_pillar_scatter.py:19-77).
+ *   w_folded (10,64) = linear.weight^T * bn_scale, b_folded (64) = bn_shift (folded on the host, fp64)
+ *   offset3_host = voxel_size/2 + range_min (x,y,z)
+ *   pillar_features_out (M,64) or NULL; canvas_nhwc_out (B,ny,nx,64) pre-zeroed, or NULL
+ *   num_voxels_dev: optional device count (row 0 used) so a graph-captured frame needs no host sync */
+int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_points, const int* voxel_coords,
+                            const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
+                            const float* w_folded, const float* b_folded, int c_in, int c_out,
+                            const float* voxel_size3_host, const float* offset3_host, int nx, int ny,
+                            float* pillar_features_out, float* canvas_nhwc_out, void* stream);
+
+/* ---- 2-D convolution, fp32 CUDA-core path ---------------------------------------------------
+ * replaces nn.Conv2d / nn.ConvTranspose2d(k==stride) + eval BatchNorm2d + ReLU (+ residual add) of
+ * resblock.py:48-64,102-122, base_bev_backbone.py:40-86, base_bev_backbone_resnet.py:54-85,
+ * downsample_conv.py:16-27, heter_pyramid_collab.py:102-107.
+ *   weight: groups==1 : [kh][kw][Cin][w_cstride] (w_cstride >= Cout, multiple of 4), BN scale folded
+ *           groups>1  : [kh*kw][Cin/groups][Cout/groups][groups] (3x3 only, Cin==Cout)
+ *   output pixel (oh,ow) of the (Ho,Wo) conv grid is stored at (oh*upsample+up_i, ow*upsample+up_j)
+ *   of an (Ho*upsample, Wo*upsample) map: a k==stride transposed conv is upsample^2 1x1 launches. */
+int heal_conv2d_nhwc_f32(const float* in, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
+                         const float* weight, int w_cstride, const float* bias,
+                         int kh, int kw, int stride, int pad, int groups,
+                         const float* residual, int res_cstride, int res_coffset,
+                         float* out, int Ho, int Wo, int Cout, int out_cstride, int out_coffset,
+                         int upsample, int up_i, int up_j, int relu, void* stream);
+
+/* ---- PyramidFusion weighted fuse of one level -------------------------------------------------
+ * replaces weighted_fuse (opencood/models/fuse_modules/pyramid_fuse.py:17-63) incl. both
+ * warp_affine_simple calls (torch_transformation_utils.py:323-332), score = sigmoid(occ)+1e-4
+ * (:145) and the eval-mode camera crop mask (:147-162) for ONE scene.
+ *   feat (n,H,W,C) channels-last; occ (n,H,W) logits; theta (n,2,3) f64 = affine_matrix[b,0,:n]
+ *   crop_windows (n,4) i32 [h0,h1,w0,w1] (score kept inside, zeroed outside) or NULL
+ *   out (H,W,C) */
+int heal_pyramid_fuse_level(const float* feat, int feat_cstride, const float* occ, const double* theta,
+                            const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
+                            float* out, int out_cstride, int out_coffset, void* stream);
+
+/* AttFusion.forward for one scene (opencood/models/fuse_modules/fusion_in_one.py:126-151) */
+int heal_att_fuse(const float* feat, int feat_cstride, const double* theta, int n_agents, int H, int W, int C,
+                  float* out, int out_cstride, int out_coffset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEAL_B200_H_ */

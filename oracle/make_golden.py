@@ -1,0 +1,123 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.pt by running the UNMODIFIED reference
+modules (imported from /root/reference through oracle/ref_shim.py) on CPU with procedural weights and
+seeded inputs.  Run in the build container only:  python -m oracle.make_golden
+The fixtures pin oracle/nets.py (tests/test_oracle_golden.py) and are the reference-derived vectors
+the CUDA path is checked against on the GPU box (tests/test_gpu_*.py)."""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+from oracle import ref_shim, procedural, voxelizer
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+SMALL_RANGE = [-12.8, -12.8, -3, 12.8, 12.8, 1]     # 64 x 64 pillars @ 0.4 m
+VOXEL = [0.4, 0.4, 4]
+
+
+def small_model_args():
+    return {
+        "lidar_range": SMALL_RANGE, "supervise_single": True,
+        "m1": {
+            "core_method": "point_pillar", "sensor_type": "lidar",
+            "encoder_args": {"voxel_size": VOXEL, "lidar_range": SMALL_RANGE,
+                             "pillar_vfe": {"use_norm": True, "with_distance": False, "use_absolute_xyz": True,
+                                            "num_filters": [64]},
+                             "point_pillar_scatter": {"num_features": 64}},
+            "backbone_args": {"layer_nums": [3], "layer_strides": [2], "num_filters": [64]},
+            "aligner_args": {"core_method": "identity"},
+        },
+        "fusion_backbone": {"resnext": True, "layer_nums": [3, 5, 8], "layer_strides": [1, 2, 2],
+                            "num_filters": [64, 128, 256], "upsample_strides": [1, 2, 4],
+                            "num_upsample_filter": [128, 128, 128], "anchor_number": 2},
+        "shrink_header": {"kernal_size": [3], "stride": [1], "padding": [1], "dim": [256], "input_dim": 384},
+        "in_head": 256, "anchor_number": 2, "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]},
+    }
+
+
+def small_scene(seed=7, n_agents=3, pts_per_agent=1500):
+    rng = np.random.default_rng(seed)
+    per_agent = []
+    for a in range(n_agents):
+        p = np.concatenate([rng.uniform(-14, 14, (pts_per_agent, 2)), rng.uniform(-3.5, 1.5, (pts_per_agent, 1)),
+                            rng.uniform(0, 1, (pts_per_agent, 1))], 1).astype(np.float32)
+        per_agent.append(voxelizer.points_to_voxel_c(p, VOXEL, SMALL_RANGE, 32, 70000))
+    col = voxelizer.collate(per_agent)
+    from heal_b200 import synth
+    poses = [[0, 0, 0, 0, 0, 0]] + [[rng.uniform(-5, 5), rng.uniform(-5, 5), 0, 0, rng.uniform(-180, 180), 0]
+                                    for _ in range(n_agents - 1)]
+    pw = synth.pairwise_t_matrix(poses, 5)[None]
+    return {
+        "inputs_m1": {k: torch.from_numpy(v) for k, v in col.items()},
+        "agent_modality_list": ["m1"] * n_agents,
+        "record_len": torch.tensor([n_agents], dtype=torch.long),
+        "pairwise_t_matrix": torch.from_numpy(pw),
+    }
+
+
+def main():
+    ref_shim.install()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from opencood.models.heter_pyramid_collab import HeterPyramidCollab
+    from opencood.models.fuse_modules.fusion_in_one import AttFusion
+    from opencood.models.sub_modules.torch_transformation_utils import warp_affine_simple
+    from opencood.models.sub_modules.base_bev_backbone import BaseBEVBackbone
+    from opencood.models.sub_modules.pillar_vfe import PillarVFE
+    from opencood.utils.transformation_utils import normalize_pairwise_tfm
+
+    # ---- 1. full HeterPyramidCollab (C2-shaped, small grid) -------------------------------------
+    args = small_model_args()
+    model = HeterPyramidCollab(copy.deepcopy(args)).eval()
+    shapes = procedural.shapes_of(model)
+    sd = procedural.make_state_dict(shapes)
+    model.load_state_dict(sd, strict=True)
+    data = small_scene()
+    with torch.no_grad():
+        dd = copy.deepcopy(data)
+        out = model(dd)
+        # intermediate: encoder + backbone features, for finer-grained parity
+        enc = model.encoder_m1(copy.deepcopy(data), "m1")
+        bb = model.backbone_m1({"spatial_features": enc})["spatial_features_2d"]
+    torch.save({
+        "args": args, "shapes": shapes, "data": data,
+        "out": {"cls_preds": out["cls_preds"], "reg_preds": out["reg_preds"], "dir_preds": out["dir_preds"],
+                "occ_single_list": out["occ_single_list"]},
+        "encoder_feature_sample": enc[:, :, ::4, ::4].contiguous(),
+        "backbone_feature": bb[:, ::4].contiguous(),
+    }, os.path.join(OUT, "heter_pyramid_collab_small.pt"))
+    print("heter_pyramid_collab_small:", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+    # ---- 2. warp_affine_simple + normalize_pairwise_tfm + AttFusion ------------------------------
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 128, 24, 40, generator=g)
+    aff = normalize_pairwise_tfm(data["pairwise_t_matrix"].clone(), 9.6, 16.0, 1)
+    with torch.no_grad():
+        w = warp_affine_simple(x, aff[0, 0, :3], (24, 40))
+        w_ac = warp_affine_simple(x, aff[0, 0, :3], (24, 40), align_corners=True)
+        att = AttFusion(128)(x, torch.tensor([3]), aff)
+    torch.save({"x": x, "pairwise_t_matrix": data["pairwise_t_matrix"], "H": 9.6, "W": 16.0, "affine": aff,
+                "warp_s": w[:, ::8].contiguous(), "warp_align_corners_s": w_ac[:, ::8].contiguous(), "att": att}, os.path.join(OUT, "warp_att.pt"))
+    print("warp_att:", tuple(w.shape), tuple(att.shape))
+
+    # ---- 3. BaseBEVBackbone [1,1,1] (AttFuse-config family, small) -------------------------------
+    cfg = {"layer_nums": [1, 2, 1], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
+           "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]}
+    bbm = BaseBEVBackbone(copy.deepcopy(cfg), 64).eval()
+    bshapes = procedural.shapes_of(bbm)
+    bbm.load_state_dict(procedural.make_state_dict(bshapes), strict=True)
+    xin = torch.randn(2, 64, 32, 48, generator=g)
+    with torch.no_grad():
+        y = bbm({"spatial_features": xin})["spatial_features_2d"]
+    torch.save({"cfg": cfg, "shapes": bshapes, "x": xin, "y_s": y[:, ::4].contiguous()}, os.path.join(OUT, "base_bev_backbone_small.pt"))
+    print("base_bev_backbone_small:", tuple(y.shape))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""Pins the oracle (oracle/nets.py) against vectors produced by the UNMODIFIED reference modules
+(oracle/make_golden.py, run in the build container).  CPU only."""
+import os
+
+import torch
+
+from oracle import nets, procedural
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_heter_pyramid_collab_small(golden_dir):
+    g = _load(golden_dir, "heter_pyramid_collab_small.pt")
+    sd = procedural.make_state_dict(g["shapes"])
+    with torch.no_grad():
+        out = nets.heter_pyramid_collab(sd, g["args"], g["data"])
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        torch.testing.assert_close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
+    for a, b in zip(out["occ_single_list"], g["out"]["occ_single_list"]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+
+
+def test_encoder_and_backbone_small(golden_dir):
+    g = _load(golden_dir, "heter_pyramid_collab_small.pt")
+    sd = procedural.make_state_dict(g["shapes"])
+    args = g["args"]
+    with torch.no_grad():
+        enc = nets.point_pillar_encoder(sd, "encoder_m1", args["m1"]["encoder_args"], g["data"]["inputs_m1"])
+        bb = nets.resnet_bev_backbone(enc, sd, "backbone_m1", args["m1"]["backbone_args"])
+    torch.testing.assert_close(enc[:, :, ::4, ::4], g["encoder_feature_sample"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(bb[:, ::4], g["backbone_feature"], rtol=1e-4, atol=1e-4)
+
+
+def test_warp_and_att(golden_dir):
+    g = _load(golden_dir, "warp_att.pt")
+    aff = nets.normalize_pairwise_tfm(g["pairwise_t_matrix"], g["H"], g["W"], 1)
+    torch.testing.assert_close(aff, g["affine"], rtol=0, atol=0)
+    w = nets.warp_affine_simple(g["x"], aff[0, 0, :3], (24, 40))
+    torch.testing.assert_close(w[:, ::8], g["warp_s"], rtol=1e-5, atol=1e-5)
+    w = nets.warp_affine_simple(g["x"], aff[0, 0, :3], (24, 40), align_corners=True)
+    torch.testing.assert_close(w[:, ::8], g["warp_align_corners_s"], rtol=1e-5, atol=1e-5)
+    att = nets.att_fusion(g["x"], torch.tensor([3]), aff)
+    torch.testing.assert_close(att, g["att"], rtol=1e-4, atol=1e-5)
+
+
+def test_base_bev_backbone_small(golden_dir):
+    g = _load(golden_dir, "base_bev_backbone_small.pt")
+    sd = procedural.make_state_dict(g["shapes"])
+    sd = {"bb." + k: v for k, v in sd.items()}
+    with torch.no_grad():
+        y = nets.base_bev_backbone(g["x"], sd, "bb", g["cfg"])
+    torch.testing.assert_close(y[:, ::4], g["y_s"], rtol=1e-4, atol=1e-4)
