@@ -1,0 +1,47 @@
+"""AttFusion / MaxFusion mirror (opencood/models/fuse_modules/fusion_in_one.py:87-151): same
+`forward(x, record_len, affine_matrix)` signature.  The other six fusion operators of that file are
+out of the hot-path scope."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+
+def regroup(x, record_len):
+    cum = torch.cumsum(record_len, dim=0)
+    return torch.tensor_split(x, cum[:-1].cpu())
+
+
+def _rl(record_len):
+    return [int(v) for v in (record_len.tolist() if torch.is_tensor(record_len) else record_len)]
+
+
+class ScaledDotProductAttention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.sqrt_dim = np.sqrt(dim)
+
+    def forward(self, query, key, value):
+        raise NotImplementedError("executed fused inside AttFusion (heal_att_fuse)")
+
+
+class AttFusion(nn.Module):
+    def __init__(self, feature_dims):
+        super().__init__()
+        self.att = ScaledDotProductAttention(feature_dims)
+        self.feature_dims = feature_dims
+
+    def forward_nhwc(self, x, record_len, affine_matrix):
+        rl = _rl(record_len)
+        _, H, W, C = x.shape
+        out = torch.empty((len(rl), H, W, C), dtype=torch.float32, device=x.device)
+        aff = affine_matrix.to(device=x.device, dtype=torch.float64)
+        start = 0
+        for b, n in enumerate(rl):
+            ops.att_fuse(x[start:start + n], aff[b, 0, :n].contiguous(), out=out[b])
+            start += n
+        return out
+
+    def forward(self, xx, record_len, affine_matrix):
+        return ops.from_nhwc(self.forward_nhwc(ops.to_nhwc(xx), record_len, affine_matrix))

@@ -1,0 +1,107 @@
+"""ResNet / ResNeXt blocks mirror (opencood/models/sub_modules/resblock.py:18-219).
+
+nn.Conv2d / nn.BatchNorm2d modules are kept only as parameter containers with the reference's
+state-dict names; forward runs each conv+BN(+residual)+ReLU as ONE kernel on NHWC buffers."""
+from typing import List, Optional
+
+import torch.nn as nn
+
+from ...engine import conv_bn_act
+
+
+def conv3x3(inp, out, stride=1, groups=1):
+    return nn.Conv2d(inp, out, 3, stride=stride, padding=1, groups=groups, bias=False)
+
+
+def conv1x1(inp, out, stride=1):
+    return nn.Conv2d(inp, out, 1, stride=stride, bias=False)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64, dilation=1, norm_layer=None):
+        super().__init__()
+        if groups != 1 or base_width != 64:
+            raise ValueError('BasicBlock only supports groups=1 and base_width=64')
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward_nhwc(self, x):
+        idt = x
+        if self.downsample is not None:
+            idt = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
+        y = conv_bn_act(x, self.conv1, self.bn1, relu=True)
+        return conv_bn_act(y, self.conv2, self.bn2, relu=True, residual=idt)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4   # PyramidFusion sets Bottleneck.expansion = 1 (pyramid_fuse.py:72)
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64, dilation=1, norm_layer=None):
+        super().__init__()
+        width = int(planes * (base_width / 64.)) * groups
+        self.conv1 = conv1x1(inplanes, width)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = conv3x3(width, width, stride, groups)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = conv1x1(width, planes * self.expansion)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward_nhwc(self, x):
+        idt = x
+        if self.downsample is not None:
+            idt = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
+        y = conv_bn_act(x, self.conv1, self.bn1, relu=True)
+        y = conv_bn_act(y, self.conv2, self.bn2, relu=True)
+        return conv_bn_act(y, self.conv3, self.bn3, relu=True, residual=idt)
+
+
+class ResNetModified(nn.Module):
+    def __init__(self, block, layers: List[int], layer_strides: List[int], num_filters: List[int],
+                 zero_init_residual=False, groups=1, width_per_group=64, replace_stride_with_dilation=None,
+                 norm_layer=None, inplanes=64):
+        super().__init__()
+        self.inplanes = inplanes
+        self.groups = groups
+        self.base_width = width_per_group
+        self.layernum = len(num_filters)
+        for i in range(self.layernum):
+            setattr(self, f"layer{i}", self._make_layer(block, num_filters[i], layers[i], layer_strides[i]))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def _make_layer(self, block, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(conv1x1(self.inplanes, planes * block.expansion, stride),
+                                       nn.BatchNorm2d(planes * block.expansion))
+        seq = [block(self.inplanes, planes, stride, downsample, self.groups, self.base_width)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            seq.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width))
+        return nn.Sequential(*seq)
+
+    def forward_nhwc(self, x):
+        feats = []
+        for i in range(self.layernum):
+            for blk in getattr(self, f"layer{i}"):
+                x = blk.forward_nhwc(x)
+            feats.append(x)
+        return feats
+
+    def forward(self, x):
+        from ... import ops
+        return [ops.from_nhwc(f) for f in self.forward_nhwc(ops.to_nhwc(x))]
