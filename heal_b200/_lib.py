@@ -13,6 +13,7 @@ _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
 SIGNATURES = {
     "heal_abi_version": (_i, []),
     "heal_device_check": (_i, []),
+    "heal_launch_count": (_c.c_longlong, []),
     "heal_voxelize_workspace": (_sz, [_i, _i, _i]),
     "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

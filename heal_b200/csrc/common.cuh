@@ -14,8 +14,12 @@
 
 #define HEAL_NUM_SMS 148  // B200: 2 dies x 74 SMs
 
-static inline int heal_check_launch() {
+// process-wide count of kernels this library has launched (bench.py reports it as gpu_launches)
+extern "C" void heal_launch_counter_add(int n);
+
+static inline int heal_check_launch(int kernels_launched = 1) {
     cudaError_t e = cudaGetLastError();
+    heal_launch_counter_add(kernels_launched);
     return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
 }
 

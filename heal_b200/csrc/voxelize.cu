@@ -322,7 +322,7 @@ extern "C" int heal_voxelize(const float* points, const int* agent_offsets, int 
     int gv = (int)(((size_t)capacity * 32 + TB - 1) / TB);
     k_select<<<gv, TB, 0, st>>>((const float4*)points, seg, cnt, seg_local, seg_blockoff, num_voxels_out,
                                 c.T, (float4*)voxels_out, num_points_out);
-    return heal_check_launch();
+    return heal_check_launch(10);
 }
 
 extern "C" int heal_mean_vfe(const float* voxels, const int* num_points, int num_voxels, int max_points_per_voxel,

@@ -47,6 +47,28 @@ def _host_i32(vals: Sequence[int]):
 
 _WS = {}
 
+# bench.py instrumentation: when PROFILE is a list, every wrapper brackets its C-ABI call with CUDA events
+# on the launching stream and appends (kernel family, algorithmic flops-or-bytes, start, end).
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.append((self.name, float(self.work), self.a, self.b))
+        return False
+
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     key = (dev.type, dev.index)
@@ -103,10 +125,11 @@ def voxelize(points: torch.Tensor, agent_offsets: torch.Tensor, lidar_range, vox
     nvox = torch.zeros((1 + A,), dtype=torch.int32, device=dev)
     ws_bytes = lib.heal_voxelize_workspace(P, cap, A)
     ws = _workspace(dev, ws_bytes)
-    rc = lib.heal_voxelize(_p(points), _p(agent_offsets), A, P,
-                           _host_f32(lidar_range[0:3]), _host_f32(voxel_size), _host_i32(grid),
-                           T, int(max_voxels), cap, _p(voxels), _p(coords), _p(npts), _p(nvox),
-                           _p(ws), ws.numel(), _stream())
+    with _Prof("voxelize", 0):
+        rc = lib.heal_voxelize(_p(points), _p(agent_offsets), A, P,
+                               _host_f32(lidar_range[0:3]), _host_f32(voxel_size), _host_i32(grid),
+                               T, int(max_voxels), cap, _p(voxels), _p(coords), _p(npts), _p(nvox),
+                               _p(ws), ws.numel(), _stream())
     check(rc, "heal_voxelize")
     return voxels, coords, npts, nvox
 
@@ -152,12 +175,13 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
     coords = voxel_coords.to(torch.int32).contiguous()
     cout = w_folded.shape[1]
     pf = torch.empty((M, cout), dtype=torch.float32, device=dev) if want_pillar_features else None
-    canvas = torch.zeros((batch_size, ny, nx, cout), dtype=torch.float32, device=dev) if want_canvas else None
     vs = [float(v) for v in voxel_size]
     off = [vs[i] / 2 + float(lidar_range[i]) for i in range(3)]
-    rc = lib.heal_pillar_vfe_scatter(_p(vf), _p(npts), _p(coords), _p(num_voxels_dev), M, T,
-                                     _p(w_folded), _p(b_folded), w_folded.shape[0], cout,
-                                     _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), _p(canvas), _stream())
+    with _Prof("pillar_vfe_scatter(+canvas memset)", 0):
+        canvas = torch.zeros((batch_size, ny, nx, cout), dtype=torch.float32, device=dev) if want_canvas else None
+        rc = lib.heal_pillar_vfe_scatter(_p(vf), _p(npts), _p(coords), _p(num_voxels_dev), M, T,
+                                         _p(w_folded), _p(b_folded), w_folded.shape[0], cout,
+                                         _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), _p(canvas), _stream())
     check(rc, "heal_pillar_vfe_scatter")
     return pf, (from_nhwc(canvas) if canvas is not None else None)
 
@@ -251,7 +275,10 @@ def conv2d(x: torch.Tensor, pc: PackedConv, residual: Optional[torch.Tensor] = N
         assert residual.is_contiguous() and residual.shape[:3] == out.shape[:3]
         res_cs = residual.shape[3]
     st = _stream()
-    for i in range(up):
+    fam = ("conv_grouped3x3_f32" if pc.groups > 1 else f"conv_dense{pc.kh}x{pc.kw}_f32")
+    flops = 2.0 * N * Ho * Wo * pc.cout * (cin // pc.groups) * pc.kh * pc.kw * up * up
+    with _Prof(fam, flops):
+      for i in range(up):
         for j in range(up):
             wptr = pc.weight if up == 1 else pc.weight[i, j]
             rc = lib.heal_conv2d_nhwc_f32(_p(x), N, H, W, cin, Cs, in_coffset, _p(wptr), pc.w_cstride, _p(pc.bias),
@@ -278,8 +305,9 @@ def pyramid_fuse_level(feat: torch.Tensor, occ: torch.Tensor, theta: torch.Tenso
         out = torch.empty((H, W, C), dtype=torch.float32, device=feat.device)
     ocs = out.shape[-1]
     cw = crop_windows.to(torch.int32).contiguous() if crop_windows is not None else None
-    rc = lib.heal_pyramid_fuse_level(_p(feat), C, _p(occ), _p(th), _p(cw), n, H, W, C, 1 if align_corners else 0,
-                                     _p(out), ocs, out_coffset, _stream())
+    with _Prof("pyramid_fuse_level", 0):
+        rc = lib.heal_pyramid_fuse_level(_p(feat), C, _p(occ), _p(th), _p(cw), n, H, W, C, 1 if align_corners else 0,
+                                         _p(out), ocs, out_coffset, _stream())
     check(rc, "heal_pyramid_fuse_level")
     return out
 

@@ -28,6 +28,8 @@ extern "C" {
 int heal_abi_version(void);
 /* sm_100a build check: returns 0 when a Blackwell (cc 10.x) device is current, negative otherwise. */
 int heal_device_check(void);
+/* number of kernels this library has launched in this process so far */
+long long heal_launch_count(void);
 
 /* ---- voxelization -------------------------------------------------------------------------
  * replaces SpVoxelPreprocessor.preprocess + collate_batch for all agents of a scene
