@@ -20,6 +20,8 @@ SIGNATURES = {
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "heal_conv2d_nhwc_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i,
                                   _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i,
+                            _vp, _sz, _vp, _i, _i, _vp, _sz, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "heal_pyramid_fuse_level": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "heal_att_fuse": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
 }

@@ -1,0 +1,432 @@
+// Implicit-GEMM 2-D convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor) with the 128-byte swizzle, warp-specialised and persistent.
+//
+// Replaces the dense convolutions of the BEV backbones / ResNeXt pyramid / shrink header
+// (reference: resblock.py:48-64,102-122; base_bev_backbone.py:40-86; base_bev_backbone_resnet.py:54-85;
+//  downsample_conv.py:16-27) with BN folded, and ReLU / residual / bias in the epilogue.
+//
+// Precision ("split-bf16", fp32-equivalent): an fp32 value x is stored as two bf16 planes hi = bf16(x),
+// lo = bf16(x - hi) (16 mantissa bits).  A product a*b is evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
+// with fp32 accumulation in TMEM: three tcgen05.mma per K step into the same accumulator, relative
+// error ~2^-16 per product, which keeps 70 stacked layers inside the 1e-3 fp32 parity tolerance that plain
+// bf16 / tf32 tensor-core math cannot meet.  With planes == 1 the same kernel is a plain bf16 conv.
+//
+// GEMM view: M = output pixels (tile = TH x TW = 128 pixels of one image), N = output channels,
+// K = taps x Cin in blocks of 64 channels.  A tile for tap (r,s) is ONE 5-D TMA box of the activation
+// tensor {C, W, H, N, plane} at (c0, w0+s-pad, h0+r-pad, n, 0); out-of-bounds elements are zero-filled
+// by the TMA unit, which implements the convolution padding.  B tiles come from the packed weights
+// {Cin, taps*CoutPad, plane}.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..5 = epilogue
+// (TMEM -> registers -> bias/residual/ReLU -> split-bf16 and/or fp32 channels-last stores).
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/heal_b200.h"
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                 // bf16 elements = 128 B = one swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB per plane
+
+struct TcP {
+    int N, Ho, Wo, Cout;          // output grid (conv resolution) and real output channels
+    int taps_w, taps, pad;        // kw, kh*kw, padding
+    int kc_blocks;                // Cin / 64
+    int TH, TW, tiles_h, tiles_w; // pixel tile and tile grid per image
+    int m_tiles, n_tiles;
+    int planes;                   // 1 = bf16, 2 = split-bf16 (fp32-equivalent)
+    int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
+    int relu;
+    int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    const float* bias;            // [Cout]
+    // residual (optional): split planes or fp32
+    const __nv_bfloat16* res_split; size_t res_plane; const float* res_f32; int res_cs, res_co;
+    // outputs (either or both)
+    __nv_bfloat16* out_split; size_t out_plane; int out_cs, out_co;
+    float* out_f32; int out32_cs, out32_co;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100): rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address (16 B units)
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                 " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024 B alignment for the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    const int stage_bytes = p.planes * (A_TILE_BYTES + B_TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int kblocks = p.taps * p.kc_blocks;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
+                const int th_i = t2 % p.tiles_h; const int img = t2 / p.tiles_h;
+                const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / p.kc_blocks, kc = kb % p.kc_blocks;
+                    const int r = tap / p.taps_w, s = tap % p.taps_w;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = sa + p.planes * A_TILE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
+                    tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 + s - p.pad, h0 + r - p.pad, img, 0);
+                    tma_load_3d(sb, &tmB, bar_full + 8 * stage, kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ================================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = sa + p.planes * A_TILE_BYTES;
+                    const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
+                    const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES), b_lo = umma_desc_sw128(sb + B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per 16-element K step
+                        const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                        if (p.planes == 2) {
+                            umma_bf16(tmem_d, a_lo + ko, b_hi + ko, idesc, first);
+                            umma_bf16(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                            umma_bf16(tmem_d, a_hi + ko, b_hi + ko, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_d, a_hi + ko, b_hi + ko, idesc, first);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * stage);       // smem slot free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);             // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;            // accumulator row = pixel within the tile
+        constexpr int CHUNK = (BLOCK_N >= 32) ? 32 : 16;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
+            const int th_i = t2 % p.tiles_h; const int img = t2 / p.tiles_h;
+            const int oh = th_i * p.TH + row / p.TW, ow = tw_i * p.TW + row % p.TW;
+            const bool valid = (oh < p.Ho) && (ow < p.Wo);
+            const int n_glob = nt * BLOCK_N;
+            const int q = n_glob / p.coutp, ch0 = n_glob % p.coutp;   // q = sub-position of a transposed conv (0 otherwise)
+            const int ui = q / p.up, uj = q % p.up;
+            const size_t pix = ((size_t)img * (p.Ho * p.up) + (size_t)(oh * p.up + ui)) * (size_t)(p.Wo * p.up) + (size_t)(ow * p.up + uj);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < BLOCK_N / CHUNK; ++cc) {
+                uint32_t raw[CHUNK];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * CHUNK);
+                if (CHUNK == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+                tmem_wait_ld();
+                const int c_first = ch0 + cc * CHUNK;
+                if (valid && c_first < p.Cout) {
+#pragma unroll
+                    for (int g8 = 0; g8 < CHUNK / 8; ++g8) {
+                        const int c = c_first + g8 * 8;
+                        if (c >= p.Cout) break;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((c + j < p.Cout && p.bias) ? __ldg(p.bias + c + j) : 0.f);
+                        const bool full8 = (c + 8 <= p.Cout);
+                        if (p.res_split) {
+                            const __nv_bfloat16* rp = p.res_split + pix * p.res_cs + p.res_co + c;
+                            if (full8 && (((p.res_cs | p.res_co) & 7) == 0)) {
+                                uint4 h = __ldg(reinterpret_cast<const uint4*>(rp));
+                                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
+                                if (p.planes == 2) {
+                                    uint4 l = __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane));
+                                    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
+                                }
+                            } else {
+                                for (int j = 0; j < 8 && c + j < p.Cout; ++j) {
+                                    v[j] += __bfloat162float(rp[j]);
+                                    if (p.planes == 2) v[j] += __bfloat162float(rp[p.res_plane + j]);
+                                }
+                            }
+                        } else if (p.res_f32) {
+                            const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
+                            for (int j = 0; j < 8 && c + j < p.Cout; ++j) v[j] += __ldg(rp + j);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (p.out_split) {
+                            __nv_bfloat16* op = p.out_split + pix * p.out_cs + p.out_co + c;
+                            float lo[8];
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float h = __bfloat162float(__float2bfloat16_rn(v[j]));
+                                lo[j] = v[j] - h;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { hw[j] = pack_bf16(v[2 * j], v[2 * j + 1]); lw[j] = pack_bf16(lo[2 * j], lo[2 * j + 1]); }
+                            if (full8 && (((p.out_cs | p.out_co) & 7) == 0)) {
+                                *reinterpret_cast<uint4*>(op) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                if (p.planes == 2) *reinterpret_cast<uint4*>(op + p.out_plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            } else {
+                                for (int j = 0; j < 8 && c + j < p.Cout; ++j) {
+                                    op[j] = __float2bfloat16_rn(v[j]);
+                                    if (p.planes == 2) op[p.out_plane + j] = __float2bfloat16_rn(lo[j]);
+                                }
+                            }
+                        }
+                        if (p.out_f32) {
+                            float* op = p.out_f32 + pix * p.out32_cs + p.out32_co + c;
+                            if (full8 && (((p.out32_cs | p.out32_co) & 3) == 0)) {
+                                stg_f4(op, make_float4(v[0], v[1], v[2], v[3]));
+                                stg_f4(op + 4, make_float4(v[4], v[5], v[6], v[7]));
+                            } else {
+                                for (int j = 0; j < 8 && c + j < p.Cout; ++j) op[j] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);          // 128 arrivals release this accumulator buffer
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmEncodeTiled get_encode() {
+    static PFN_tmEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmEncodeTiled)f;
+    }
+    return fn;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& p, cudaStream_t st) {
+    size_t smem = 1024 + (size_t)STAGES * p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_conv2d_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+            return HEAL_ERR_LAUNCH;
+        attr_set = true;
+    }
+    int total = p.m_tiles * p.n_tiles;
+    int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
+    k_conv2d_tc<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    return heal_check_launch();
+}
+
+}  // namespace
+
+extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
+                              const void* w_packed, int w_rows, int coutp, const float* bias,
+                              int kh, int kw, int pad, int planes,
+                              const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
+                              void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
+                              float* out_f32, int out32_cstride, int out32_coffset,
+                              int Ho, int Wo, int Cout, int upsample, int relu, void* stream_) {
+    if (!in_split || !w_packed || (!out_split && !out_f32)) return HEAL_ERR_ARG;
+    if (planes != 1 && planes != 2) return HEAL_ERR_ARG;
+    if ((Cin % BLOCK_K) || (in_cstride & 7) || (in_coffset & 7) || upsample < 1) return HEAL_ERR_UNSUPPORTED;
+    if (Ho != H + 2 * pad - kh + 1 || Wo != W + 2 * pad - kw + 1) return HEAL_ERR_UNSUPPORTED;   // stride 1 only
+    if (upsample > 1 && (kh != 1 || kw != 1)) return HEAL_ERR_UNSUPPORTED;
+    const int taps = kh * kw;
+    const int block_n = coutp >= 128 ? 128 : coutp;
+    if (!(block_n == 16 || block_n == 32 || block_n == 64 || block_n == 128) || (coutp % block_n)) return HEAL_ERR_UNSUPPORTED;
+    if (w_rows != (upsample > 1 ? upsample * upsample : taps) * coutp) return HEAL_ERR_ARG;
+    PFN_tmEncodeTiled enc = get_encode();
+    if (!enc) return HEAL_ERR_DRIVER;
+
+    TcP p;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+    p.taps_w = kw; p.taps = taps; p.pad = pad; p.kc_blocks = Cin / BLOCK_K;
+    int tw = 128; while (tw > Wo && tw > 8) tw >>= 1;
+    p.TW = tw; p.TH = BLOCK_M / tw;
+    p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
+    p.m_tiles = N * p.tiles_h * p.tiles_w;
+    p.n_tiles = w_rows / taps / block_n * (upsample > 1 ? 1 : 1);
+    if (upsample > 1) p.n_tiles = w_rows / block_n;
+    p.planes = planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
+    p.res_split = (const __nv_bfloat16*)res_split; p.res_plane = res_plane_stride; p.res_f32 = res_f32;
+    p.res_cs = res_cstride; p.res_co = res_coffset;
+    p.out_split = (__nv_bfloat16*)out_split; p.out_plane = out_plane_stride; p.out_cs = out_cstride; p.out_co = out_coffset;
+    p.out_f32 = out_f32; p.out32_cs = out32_cstride; p.out32_co = out32_coffset;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)planes};
+        cuuint64_t strides[4] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)W * in_cstride * 2, (cuuint64_t)H * W * in_cstride * 2,
+                                 (cuuint64_t)in_plane_stride * 2};
+        cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1u, (cuuint32_t)planes};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        void* base = (void*)((const __nv_bfloat16*)in_split + in_coffset);
+        if (planes == 1) { strides[3] = strides[2] * N; }
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)w_rows, (cuuint64_t)planes};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)w_rows * Cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, (cuuint32_t)planes};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
+    }
+    cudaStream_t st = (cudaStream_t)stream_;
+    switch (block_n) {
+        case 16: return launch_tc<16, 4>(tmA, tmB, p, st);
+        case 32: return launch_tc<32, 4>(tmA, tmB, p, st);
+        case 64: return launch_tc<64, 4>(tmA, tmB, p, st);
+        default: return launch_tc<128, 3>(tmA, tmB, p, st);
+    }
+}

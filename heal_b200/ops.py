@@ -323,3 +323,100 @@ def att_fuse(feat: torch.Tensor, theta: torch.Tensor, out: Optional[torch.Tensor
     rc = lib.heal_att_fuse(_p(feat), C, _p(th), n, H, W, C, _p(out), out.shape[-1], 0, _stream())
     check(rc, "heal_att_fuse")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# conv2d, tcgen05 tensor-core path (split-bf16 activations)
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor, planes: int = 2) -> torch.Tensor:
+    """fp32 (...,) -> bf16 (planes, ...) with hi = bf16(x), lo = bf16(x - hi)  (host-side / test helper)."""
+    hi = x.to(torch.bfloat16)
+    if planes == 1:
+        return hi.unsqueeze(0).contiguous()
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def merge_bf16(s: torch.Tensor) -> torch.Tensor:
+    return s.float().sum(0)
+
+
+def _coutp(cout: int) -> int:
+    for c in (16, 32, 64):
+        if cout <= c:
+            return c
+    return (cout + 127) // 128 * 128
+
+
+class PackedConvTC:
+    def __init__(self, w, bias, kh, kw, pad, cin, cout, coutp, relu, up, planes):
+        self.w, self.bias = w, bias
+        self.kh, self.kw, self.pad, self.cin, self.cout, self.coutp = kh, kw, pad, cin, cout, coutp
+        self.relu, self.up, self.planes = relu, up, planes
+
+    def to(self, device):
+        self.w = self.w.to(device)
+        self.bias = self.bias.to(device)
+        return self
+
+
+def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> PackedConvTC:
+    """Fold BN (fp64), lay weights out as [plane][tap*coutp + co][Cin] split-bf16 for heal_conv2d_tc."""
+    scale_shift = _bn_scale_shift
+    if isinstance(conv, torch.nn.ConvTranspose2d):
+        w = conv.weight.detach().double().cpu()            # (Cin, Cout, k, k)
+        cin, cout, k, _ = w.shape
+        scale, shift = scale_shift(bn, cout)
+        b = shift + (conv.bias.detach().double().cpu() * scale if conv.bias is not None else 0)
+        w = w * scale[None, :, None, None]
+        coutp = _coutp(cout)
+        rows = torch.zeros((k * k, coutp, cin), dtype=torch.float64)
+        rows[:, :cout, :] = w.permute(2, 3, 1, 0).reshape(k * k, cout, cin)
+        wp = split_bf16(rows.reshape(k * k * coutp, cin).float(), planes)
+        return PackedConvTC(wp, b.float().contiguous(), 1, 1, 0, cin, cout, coutp, relu, k, planes)
+    w = conv.weight.detach().double().cpu()                # (Cout, Cin, kh, kw)
+    cout, cin, kh, kw = w.shape
+    assert conv.groups == 1 and conv.stride == (1, 1)
+    scale, shift = scale_shift(bn, cout)
+    b = shift + (conv.bias.detach().double().cpu() * scale if conv.bias is not None else 0)
+    w = w * scale[:, None, None, None]
+    coutp = _coutp(cout)
+    rows = torch.zeros((kh * kw, coutp, cin), dtype=torch.float64)
+    rows[:, :cout, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    wp = split_bf16(rows.reshape(kh * kw * coutp, cin).float(), planes)
+    return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, cin, cout, coutp, relu, 1, planes)
+
+
+def conv2d_tc(x_split: torch.Tensor, pc: PackedConvTC, residual_split: Optional[torch.Tensor] = None,
+              residual_f32: Optional[torch.Tensor] = None, want_split: bool = True, want_f32: bool = False,
+              out_split: Optional[torch.Tensor] = None, out_coffset: int = 0, in_coffset: int = 0,
+              out_f32: Optional[torch.Tensor] = None, out32_coffset: int = 0):
+    """x_split: bf16 (planes,N,H,W,Cs).  Returns (out_split | None, out_f32 | None)."""
+    _need_cuda(x_split, pc.w)
+    P, N, H, W, Cs = x_split.shape
+    assert P == pc.planes and x_split.dtype == torch.bfloat16 and x_split.is_contiguous()
+    up = pc.up
+    Ho, Wo = H + 2 * pc.pad - pc.kh + 1, W + 2 * pc.pad - pc.kw + 1
+    dev = x_split.device
+    if want_split and out_split is None:
+        out_split = torch.empty((P, N, Ho * up, Wo * up, pc.cout), dtype=torch.bfloat16, device=dev)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((N, Ho * up, Wo * up, pc.cout), dtype=torch.float32, device=dev)
+    res_cs = 0
+    res_plane = 0
+    if residual_split is not None:
+        res_cs, res_plane = residual_split.shape[-1], residual_split[0].numel()
+    elif residual_f32 is not None:
+        res_cs = residual_f32.shape[-1]
+    fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "")
+    flops = 2.0 * N * Ho * Wo * pc.cout * pc.cin * pc.kh * pc.kw * up * up
+    with _Prof(fam, flops):
+        rc = lib.heal_conv2d_tc(_p(x_split), x_split[0].numel(), N, H, W, pc.cin, Cs, in_coffset,
+                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.pad, P,
+                                _p(residual_split), res_plane, _p(residual_f32), res_cs, 0,
+                                _p(out_split), out_split[0].numel() if out_split is not None else 0,
+                                out_split.shape[-1] if out_split is not None else 0, out_coffset,
+                                _p(out_f32), out_f32.shape[-1] if out_f32 is not None else 0, out32_coffset,
+                                Ho, Wo, pc.cout, up, 1 if pc.relu else 0, _stream())
+    check(rc, "heal_conv2d_tc")
+    return out_split, out_f32

@@ -82,6 +82,24 @@ int heal_conv2d_nhwc_f32(const float* in, int N, int H, int W, int Cin, int in_c
                          float* out, int Ho, int Wo, int Cout, int out_cstride, int out_coffset,
                          int upsample, int up_i, int up_j, int relu, void* stream);
 
+/* ---- 2-D convolution, tcgen05 tensor-core path (stride 1) ---------------------------------------
+ * Same reference ops as heal_conv2d_nhwc_f32, evaluated as an implicit GEMM with tcgen05.mma (TMEM
+ * accumulators) fed by TMA.  Activations are "split-bf16": `planes` bf16 channels-last planes
+ * (planes=2: hi = bf16(x), lo = bf16(x-hi), fp32-equivalent via 3 MMAs per K step; planes=1: plain bf16).
+ *   in_split   bf16 [planes][N][H][W][in_cstride], plane stride in elements; Cin % 64 == 0
+ *   w_packed   bf16 [planes][w_rows][Cin]; conv: w_rows = kh*kw*coutp, row = tap*coutp + co;
+ *              transposed conv (kh=kw=1, upsample=k): w_rows = k*k*coutp, row = (i*k+j)*coutp + co;
+ *              coutp = Cout padded to 16/32/64 or a multiple of 128; BN scale folded; bias fp32 [Cout]
+ *   residual   split planes (res_split) or fp32 (res_f32) or neither, at output resolution
+ *   outputs    split planes and/or fp32, channels-last, output map (Ho*upsample, Wo*upsample) */
+int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
+                   const void* w_packed, int w_rows, int coutp, const float* bias,
+                   int kh, int kw, int pad, int planes,
+                   const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
+                   void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
+                   float* out_f32, int out32_cstride, int out32_coffset,
+                   int Ho, int Wo, int Cout, int upsample, int relu, void* stream);
+
 /* ---- PyramidFusion weighted fuse of one level -------------------------------------------------
  * replaces weighted_fuse (opencood/models/fuse_modules/pyramid_fuse.py:17-63) incl. both
  * warp_affine_simple calls (torch_transformation_utils.py:323-332), score = sigmoid(occ)+1e-4

@@ -1,0 +1,98 @@
+"""tcgen05 implicit-GEMM conv (heal_conv2d_tc) vs PyTorch CPU fp32, ordered from a bare GEMM tile to full features.
+fp32-equivalent (split-bf16, planes=2) must meet 1e-3 (typically ~2e-5); bf16 (planes=1) must meet 1e-2 relative to scale."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, N, Cin, H, W, Cout, k, pad, bias, bn, relu, res ('none'|'split'|'f32')
+    ("gemm_1tile", 1, 64, 1, 128, 64, 1, 0, False, False, False, "none"),
+    ("gemm_k128", 1, 128, 1, 128, 64, 1, 0, False, False, False, "none"),
+    ("gemm_2rows", 1, 64, 2, 128, 64, 1, 0, False, False, False, "none"),
+    ("gemm_n128", 1, 64, 4, 128, 128, 1, 0, False, False, False, "none"),
+    ("gemm_n256_persist", 2, 128, 64, 128, 256, 1, 0, True, False, True, "none"),
+    ("conv3x3_basic", 1, 64, 8, 128, 64, 3, 1, False, False, False, "none"),
+    ("conv3x3_w64", 2, 64, 16, 64, 64, 3, 1, False, True, True, "split"),
+    ("conv3x3_w16", 1, 128, 16, 16, 128, 3, 1, True, False, True, "f32"),
+    ("conv3x3_shrink", 1, 384, 32, 32, 256, 3, 1, True, False, True, "none"),
+    ("conv3x3_ragged", 1, 64, 19, 40, 64, 3, 1, False, True, True, "split"),
+    ("conv1x1_n16", 1, 64, 8, 64, 1, 1, 0, True, False, False, "none"),
+    ("conv1x1_n32", 1, 256, 8, 64, 20, 1, 0, True, False, False, "none"),
+    ("conv1x1_big", 5, 64, 64, 128, 128, 1, 0, False, True, True, "none"),
+]
+
+
+def _mk(case):
+    name, N, Cin, H, W, Cout, k, pad, bias, bn, relu, res = case
+    gen = torch.Generator().manual_seed(abs(hash(name)) % 10000)
+    conv = torch.nn.Conv2d(Cin, Cout, k, padding=pad, bias=bias)
+    bnm = torch.nn.BatchNorm2d(Cout, eps=1e-3).eval() if bn else None
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * (1.0 / (Cin * k * k)) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(Cout, generator=gen) * 0.1)
+        if bn:
+            bnm.weight.copy_(torch.rand(Cout, generator=gen) + 0.5)
+            bnm.bias.copy_(torch.randn(Cout, generator=gen) * 0.1)
+            bnm.running_mean.copy_(torch.randn(Cout, generator=gen) * 0.1)
+            bnm.running_var.copy_(torch.rand(Cout, generator=gen) + 0.5)
+    x = torch.randn(N, Cin, H, W, generator=gen)
+    with torch.no_grad():
+        y = conv(x)
+        if bn:
+            y = bnm(y)
+        r = torch.randn(y.shape, generator=gen) if res != "none" else None
+        if r is not None:
+            y = y + r
+        if relu:
+            y = F.relu(y)
+    return conv, bnm, x, r, y
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("planes", [2, 1])
+def test_conv_tc(case, planes):
+    from heal_b200 import ops
+    name, N, Cin, H, W, Cout, k, pad, bias, bn, relu, res = case
+    conv, bnm, x, r, y = _mk(case)
+    pc = ops.pack_conv_tc(conv, bnm, relu, planes=planes).to("cuda")
+    xs = ops.split_bf16(ops.to_nhwc(x.cuda()), planes)
+    rs = ops.split_bf16(ops.to_nhwc(r.cuda()), planes) if res == "split" else None
+    rf = ops.to_nhwc(r.cuda()) if res == "f32" else None
+    o_split, o_f32 = ops.conv2d_tc(xs, pc, residual_split=rs, residual_f32=rf, want_split=True, want_f32=True)
+    torch.cuda.synchronize()
+    got32 = o_f32.permute(0, 3, 1, 2).cpu()
+    gots = ops.merge_bf16(o_split).permute(0, 3, 1, 2).cpu()
+    scale = y.abs().max().item()
+    e32 = (got32 - y).abs().max().item()
+    es = (gots - y).abs().max().item()
+    print(f"{name} planes={planes}: max|y|={scale:.3f} err_f32out={e32:.3e} err_splitout={es:.3e}")
+    tol = 1e-3 if planes == 2 else 3e-2 * max(scale, 1.0)
+    assert e32 < tol and es < (tol if planes == 2 else tol + 1e-2 * max(scale, 1.0))
+
+
+@pytest.mark.parametrize("up", [1, 2, 4])
+def test_deconv_tc(up):
+    from heal_b200 import ops
+    gen = torch.Generator().manual_seed(up)
+    cin = {1: 64, 2: 128, 4: 256}[up]
+    de = torch.nn.ConvTranspose2d(cin, 128, up, stride=up, bias=False)
+    bnm = torch.nn.BatchNorm2d(128, eps=1e-3).eval()
+    with torch.no_grad():
+        de.weight.copy_(torch.randn(de.weight.shape, generator=gen) * (1.0 / cin) ** 0.5)
+        bnm.running_mean.copy_(torch.randn(128, generator=gen) * 0.1)
+        bnm.running_var.copy_(torch.rand(128, generator=gen) + 0.5)
+    x = torch.randn(2, cin, 16, 32, generator=gen)
+    with torch.no_grad():
+        y = F.relu(bnm(de(x)))
+    pc = ops.pack_conv_tc(de, bnm, True, planes=2).to("cuda")
+    xs = ops.split_bf16(ops.to_nhwc(x.cuda()), 2)
+    buf = torch.zeros((2, 2, 16 * up, 32 * up, 384), dtype=torch.bfloat16, device="cuda")
+    ops.conv2d_tc(xs, pc, out_split=buf, out_coffset=128, want_split=True)
+    got = ops.merge_bf16(buf)[..., 128:256].permute(0, 3, 1, 2).cpu()
+    err = (got - y).abs().max().item()
+    print(f"deconv up={up}: err={err:.3e}")
+    assert err < 1e-3
+    assert torch.all(buf[..., :128] == 0) and torch.all(buf[..., 256:] == 0)
