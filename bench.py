@@ -127,6 +127,34 @@ def build_scenes(n_scenes, n_agents, seed0=100):
     return scenes
 
 
+def pick_host_threads():
+    """Pick the PyTorch-CPU thread count that is actually fastest on this box (containers often expose more
+    logical CPUs than their quota; 128 threads on a throttled cgroup is 10x slower than 16)."""
+    import torch
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            avail = max(1, min(avail, int(int(q[0]) / int(q[1]))))
+    except Exception:
+        pass
+    cands = sorted({c for c in (8, 16, 32, 64, 128, avail) if c <= avail})
+    x = torch.randn(1, 64, 256, 256)
+    w = torch.randn(64, 64, 3, 3)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_frame(sd, args, scene, n_agents):
     """One frame on the CPU through the oracle (restated voxelizer in C + fp32 PyTorch-CPU dense path)."""
     import torch
@@ -150,8 +178,7 @@ def run_reference(opt):
         return
     from oracle import procedural, voxelizer
     voxelizer.build_c()
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_host_threads()
     args = model_args()
     from heal_b200.models.heter_pyramid_collab import HeterPyramidCollab
     shapes = procedural.shapes_of(HeterPyramidCollab(copy.deepcopy(args)))
@@ -167,7 +194,7 @@ def run_reference(opt):
     line = {"metric": "frames/sec (5-agent OPV2V scene)", "value": fps, "unit": "frames/s", "n_gpus": opt.gpus,
             "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": 1000 * dt / opt.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(1, "cpu"),
+            "config": workload_config(1, "cpu", "fp32"),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "whole 5-agent frame per step (restated C voxelizer + PyTorch-CPU fp32 dense path)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -175,12 +202,20 @@ def run_reference(opt):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, parallelism):
+PRECISION_TEXT = {
+    "tc32": "fp32-equivalent: split-bf16 operands (hi+lo planes), 3 tcgen05 MMAs per K-step, fp32 accumulate in TMEM; "
+            "grouped/strided convs and fusion in fp32 FMA",
+    "bf16": "bf16 operands on tcgen05, fp32 accumulate",
+    "fp32": "fp32 storage, fp32 FMA on CUDA cores",
+}
+
+
+def workload_config(n_gpus, parallelism, precision="tc32"):
     return {"workload": "configs[1]: heter_pyramid_collab (PointPillars m1 + PyramidFusion ResNeXt), 5 agents x 64-line LiDAR "
                         "(~58k pts/agent), range +-102.4 m, 512x512 pillars @0.4 m, fusion map 256x256, batch 1 scene",
             "parallelism": parallelism if n_gpus > 1 else "single-gpu",
             "l2_policy": "per-frame working set (~1.5 GB activations) >> 126 MB L2; scenes rotate so no frame reuses inputs",
-            "precision": "fp32 storage; fp32 FMA accumulate"}
+            "precision": PRECISION_TEXT[precision]}
 
 
 def main():
@@ -191,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="heal_b200")
     ap.add_argument("--parallelism", default="scene", choices=["scene", "agent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tc32", choices=["tc32", "bf16", "fp32"])
     opt = ap.parse_args()
     opt.warmup = max(opt.warmup, 3) if opt.impl != "reference" else opt.warmup
     if opt.impl == "reference":
@@ -206,9 +242,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from heal_b200._lib import lib
-    from heal_b200 import ops
+    from heal_b200 import ops, engine
     from heal_b200.models.heter_pyramid_collab import HeterPyramidCollab
     from oracle import procedural   # deterministic parameter table only (no oracle compute on this path)
+    engine.set_precision(opt.precision)
 
     n_agents = N_AGENTS if (opt.parallelism == "scene" or world == 1) else world
     args = model_args(max_cav=max(5, n_agents))
@@ -324,27 +361,31 @@ def main():
         roofline = None
         if dom[0] is not None:
             ach = dom[1]["tflops"]
+            mma_per_flop = 3 if (opt.precision == "tc32" and dom[0].startswith("conv_tc")) else 1
             roofline = {"bound": "tensor", "kernel": dom[0], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach / peak_tf if ach else None, "traffic": None, "peak_source": peak_src,
+                        "note": "achieved = ALGORITHMIC conv FLOPs / CUDA-event time of that kernel family; in tc32 mode every "
+                                "algorithmic FLOP issues 3 bf16 tensor-core FLOPs (tensor_pipe_tflops = 3 x achieved)",
+                        "tensor_pipe_tflops": ach * mma_per_flop if ach else None,
+                        "tensor_pipe_frac": ach * mma_per_flop / peak_tf if ach else None,
                         "ms_per_frame": dom[1]["ms_per_frame"], "share_of_step": dom[1]["ms_per_frame"] / (total_ms / opt.steps),
                         "all_kernels": prof}
         cpu = None
         if not opt.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
+            cores = pick_host_threads()
             from oracle import voxelizer
             voxelizer.build_c()
             cpu_sd = {k: v.cpu() for k, v in sd.items()}
-            _, tv, tn = cpu_frame(cpu_sd, args, scenes[0], n_agents)    # warm
             _, tv, tn = cpu_frame(cpu_sd, args, scenes[1], n_agents)
             cpu = {"value": 1.0 / (tv + tn), "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"1 whole frame ({n_agents} agents) after 1 warm-up frame: voxelize {tv*1e3:.0f} ms (restated C, 1 thread) + "
-                             f"network {tn*1e3:.0f} ms (PyTorch-CPU fp32, {cores} threads)"}
+                   "sample": f"1 whole frame ({n_agents} agents), no warm-up: voxelize {tv*1e3:.0f} ms (restated C, 1 thread) + "
+                             f"network {tn*1e3:.0f} ms (PyTorch-CPU fp32, {cores} threads chosen by a conv micro-calibration)"}
         line = {"metric": "frames/sec (5-agent OPV2V scene)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": total_ms / opt.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"tc32": "f32", "bf16": "bf16", "fp32": "f32"}[opt.precision],
+                "data": "synthetic",
                 "config": workload_config(world, "scene-replicas (1 scene stream per GPU, no collective)" if opt.parallelism == "scene"
-                                          else "agent-per-GPU + 1 NCCL all-gather"),
+                                          else "agent-per-GPU + 1 NCCL all-gather", opt.precision),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "gflop_per_frame": frame_flops(n_agents) / 1e9}

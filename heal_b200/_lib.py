@@ -9,6 +9,14 @@ LIB_PATH = os.path.join(_HERE, "libheal_b200.so")
 _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
 
+
+class HealAct(ctypes.Structure):
+    """heal_act_t of include/heal_b200.h"""
+    _fields_ = [("data", _vp), ("fmt", _i), ("cstride", _i), ("coffset", _i), ("plane_stride", _sz)]
+
+
+_ap = ctypes.POINTER(HealAct)
+
 # name -> (restype, argtypes); must list every symbol include/heal_b200.h declares
 SIGNATURES = {
     "heal_abi_version": (_i, []),
@@ -18,12 +26,13 @@ SIGNATURES = {
     "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "heal_conv2d_nhwc_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i,
-                                  _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "heal_conv2d_simt": (_i, [_ap, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _ap, _ap, _i, _i, _i,
+                              _i, _i, _i, _i, _vp]),
     "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i,
                             _vp, _sz, _vp, _i, _i, _vp, _sz, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "heal_pyramid_fuse_level": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
-    "heal_att_fuse": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "heal_pyramid_fuse_level": (_i, [_ap, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ap, _vp]),
+    "heal_att_fuse": (_i, [_ap, _vp, _i, _i, _i, _i, _ap, _vp]),
+    "heal_act_convert": (_i, [_ap, _ap, _sz, _i, _vp]),
 }
 
 ERRORS = {-1: "HEAL_ERR_ARG", -2: "HEAL_ERR_WORKSPACE", -3: "HEAL_ERR_LAUNCH", -4: "HEAL_ERR_UNSUPPORTED",

@@ -54,3 +54,63 @@ __device__ __forceinline__ int warp_min_i(int v) {
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ---- activation views: fp32, bf16 (one plane) or split-bf16 (hi + lo planes), channels-last ----------
+// Mirrors heal_act_t of include/heal_b200.h.
+struct ActV {
+    void* p;
+    int fmt;        // 0 = f32, 1 = bf16, 2 = split-bf16
+    int cs, co;     // pixel stride / first channel (elements)
+    size_t plane;   // elements between hi and lo plane (fmt 2)
+};
+
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 u) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    return u;
+}
+// 4 consecutive channels starting at channel c (multiple of 4) of pixel `pix`
+__device__ __forceinline__ float4 act_load4(const ActV& a, size_t pix, int c) {
+    size_t idx = pix * (size_t)a.cs + (size_t)(a.co + c);
+    if (a.fmt == 0) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.p) + idx));
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(a.p) + idx;
+    float4 v = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(b)));
+    if (a.fmt == 2) {
+        float4 l = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(b + a.plane)));
+        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+    }
+    return v;
+}
+__device__ __forceinline__ void act_store4(const ActV& a, size_t pix, int c, float4 v) {
+    size_t idx = pix * (size_t)a.cs + (size_t)(a.co + c);
+    if (a.fmt == 0) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.p) + idx) = v; return; }
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(a.p) + idx;
+    uint2 h = f4_to_bf16x4(v);
+    *reinterpret_cast<uint2*>(b) = h;
+    if (a.fmt == 2) {
+        float4 hf = bf16x4_to_f4(h);
+        *reinterpret_cast<uint2*>(b + a.plane) = f4_to_bf16x4(make_float4(v.x - hf.x, v.y - hf.y, v.z - hf.z, v.w - hf.w));
+    }
+}
+__device__ __forceinline__ float act_load1(const ActV& a, size_t pix, int c) {
+    size_t idx = pix * (size_t)a.cs + (size_t)(a.co + c);
+    if (a.fmt == 0) return __ldg(reinterpret_cast<const float*>(a.p) + idx);
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(a.p) + idx;
+    float v = __bfloat162float(b[0]);
+    if (a.fmt == 2) v += __bfloat162float(b[a.plane]);
+    return v;
+}
+__device__ __forceinline__ void act_store1(const ActV& a, size_t pix, int c, float v) {
+    size_t idx = pix * (size_t)a.cs + (size_t)(a.co + c);
+    if (a.fmt == 0) { reinterpret_cast<float*>(a.p)[idx] = v; return; }
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(a.p) + idx;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    b[0] = h;
+    if (a.fmt == 2) b[a.plane] = __float2bfloat16_rn(v - __bfloat162float(h));
+}

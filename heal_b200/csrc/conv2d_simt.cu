@@ -13,10 +13,10 @@
 namespace {
 
 struct ConvP {
-    const float* in; const float* w; const float* bias; const float* res; float* out;
-    int N, H, W, Cin, in_cs, in_co;          // input: channels used = Cin, pixel stride in_cs, channel offset in_co
-    int Ho, Wo, Cout, out_cs, out_co;        // conv output grid (Ho,Wo); memory pixel stride / channel offset
-    int res_cs, res_co;
+    ActV in, res, out;                       // activation views (fp32 / bf16 / split-bf16); res.p == nullptr when unused
+    const float* w; const float* bias;
+    int N, H, W, Cin;
+    int Ho, Wo, Cout;                        // conv output grid (Ho,Wo)
     int kh, kw, stride, pad;
     int w_cs;                                // weight row stride (>= Cout, multiple of 4)
     int relu;
@@ -65,8 +65,7 @@ k_conv2d_dense(ConvP p) {
                     int ih = lp_h[j] * p.stride - p.pad + r, iw = lp_w[j] * p.stride - p.pad + s;
                     int ci = c0 + kq * 4;
                     if (lp_ok[j] && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && ci < p.Cin) {
-                        const float* src = p.in + ((size_t)((size_t)lp_n[j] * p.H + ih) * p.W + iw) * p.in_cs + p.in_co + ci;
-                        v = ldg_f4(src);
+                        v = act_load4(p.in, (size_t)((size_t)lp_n[j] * p.H + ih) * p.W + iw, ci);
                     }
                     int m = tid / 4 + 64 * j;
                     As[kq * 4 + 0][m] = v.x; As[kq * 4 + 1][m] = v.y; As[kq * 4 + 2][m] = v.z; As[kq * 4 + 3][m] = v.w;
@@ -116,21 +115,19 @@ k_conv2d_dense(ConvP p) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
-        if (p.res) {
-            const float* rp = p.res + pix * p.res_cs + p.res_co + co;
+        if (p.res.p) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (co + j < p.Cout) v[j] += rp[j];
+            for (int j = 0; j < 4; ++j) if (co + j < p.Cout) v[j] += act_load1(p.res, pix, co + j);
         }
         if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        float* op = p.out + pix * p.out_cs + p.out_co + co;
-        if (co + 3 < p.Cout && ((p.out_cs | p.out_co) & 3) == 0) {
-            stg_f4(op, make_float4(v[0], v[1], v[2], v[3]));
+        if (co + 3 < p.Cout && ((p.out.cs | p.out.co) & 3) == 0) {
+            act_store4(p.out, pix, co, make_float4(v[0], v[1], v[2], v[3]));
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (co + j < p.Cout) op[j] = v[j];
+            for (int j = 0; j < 4; ++j) if (co + j < p.Cout) act_store1(p.out, pix, co + j, v[j]);
         }
     }
 }
@@ -178,10 +175,10 @@ k_conv2d_grouped(ConvP p) {
                 for (int i = 0; i < PX; ++i) {
                     int iw = (ow0 + i) * p.stride - p.pad + s;
                     bool ok = (iw >= 0 && iw < p.W && ow0 + i < p.Wo);
-                    const float* src = p.in + ((size_t)((size_t)n * p.H + ih) * p.W + (ok ? iw : 0)) * p.in_cs + p.in_co + g * CG;
+                    const size_t ipix = (size_t)((size_t)n * p.H + ih) * p.W + (ok ? iw : 0);
 #pragma unroll
                     for (int q = 0; q < CG / 4; ++q) {
-                        float4 v = ok ? ldg_f4(src + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 v = ok ? act_load4(p.in, ipix, g * CG + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                         x[i][q * 4 + 0] = v.x; x[i][q * 4 + 1] = v.y; x[i][q * 4 + 2] = v.z; x[i][q * 4 + 3] = v.w;
                     }
                 }
@@ -201,7 +198,6 @@ k_conv2d_grouped(ConvP p) {
             int ow = ow0 + i;
             if (ow >= p.Wo) break;
             size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
-            float* op = p.out + pix * p.out_cs + p.out_co + g * CG + co0;
 #pragma unroll
             for (int q = 0; q < COC / 4; ++q) {
                 float v[4];
@@ -210,7 +206,7 @@ k_conv2d_grouped(ConvP p) {
                     float t = acc[i][q * 4 + j] + bv[q * 4 + j];
                     v[j] = p.relu ? fmaxf(t, 0.f) : t;
                 }
-                stg_f4(op + q * 4, make_float4(v[0], v[1], v[2], v[3]));
+                act_store4(p.out, pix, g * CG + co0 + q * 4, make_float4(v[0], v[1], v[2], v[3]));
             }
         }
     }
@@ -235,20 +231,27 @@ int launch_grouped(const ConvP& p, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int heal_conv2d_nhwc_f32(const float* in, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
-                                    const float* weight, int w_cstride, const float* bias,
-                                    int kh, int kw, int stride, int pad, int groups,
-                                    const float* residual, int res_cstride, int res_coffset,
-                                    float* out, int Ho, int Wo, int Cout, int out_cstride, int out_coffset,
-                                    int upsample, int up_i, int up_j, int relu, void* stream_) {
-    if (!in || !weight || !out) return HEAL_ERR_ARG;
+static inline ActV to_view(const heal_act_t* a) {
+    ActV v;
+    if (!a) { v.p = nullptr; v.fmt = 0; v.cs = 0; v.co = 0; v.plane = 0; return v; }
+    v.p = a->data; v.fmt = a->fmt; v.cs = a->cstride; v.co = a->coffset; v.plane = a->plane_stride;
+    return v;
+}
+
+extern "C" int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
+                                const float* weight, int w_cstride, const float* bias,
+                                int kh, int kw, int stride, int pad, int groups,
+                                const heal_act_t* residual, const heal_act_t* out, int Ho, int Wo, int Cout,
+                                int upsample, int up_i, int up_j, int relu, void* stream_) {
+    if (!in || !in->data || !weight || !out || !out->data) return HEAL_ERR_ARG;
     if (N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || Ho < 1 || Wo < 1 || stride < 1 || upsample < 1) return HEAL_ERR_ARG;
-    if ((in_cstride & 3) || (in_coffset & 3) || (Cin & 3)) return HEAL_ERR_UNSUPPORTED;
+    if ((in->cstride & 3) || (in->coffset & 3) || (Cin & 3)) return HEAL_ERR_UNSUPPORTED;
+    if (in->fmt < 0 || in->fmt > 2 || out->fmt < 0 || out->fmt > 2) return HEAL_ERR_ARG;
     ConvP p;
-    p.in = in; p.w = weight; p.bias = bias; p.res = residual; p.out = out;
-    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.in_cs = in_cstride; p.in_co = in_coffset;
-    p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.out_cs = out_cstride; p.out_co = out_coffset;
-    p.res_cs = res_cstride; p.res_co = res_coffset;
+    p.in = to_view(in); p.res = to_view(residual); p.out = to_view(out);
+    p.w = weight; p.bias = bias;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin;
+    p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.w_cs = w_cstride; p.relu = relu;
     p.up = upsample; p.up_i = up_i; p.up_j = up_j; p.groups = groups;
     cudaStream_t st = (cudaStream_t)stream_;
@@ -259,9 +262,9 @@ extern "C" int heal_conv2d_nhwc_f32(const float* in, int N, int H, int W, int Ci
         k_conv2d_dense<<<grid, 256, 0, st>>>(p);
         return heal_check_launch();
     }
-    // grouped: 3x3, Cin == Cout, CG = Cin/groups in {4,8,16}, dense channel layouts, no residual/upsample
+    // grouped: 3x3, Cin == Cout, CG = Cin/groups in {4,8,16}, no residual/upsample
     if (kh != 3 || kw != 3 || Cin != Cout || residual || upsample != 1 || (groups % 32) != 0) return HEAL_ERR_UNSUPPORTED;
-    if ((out_cstride & 3) || (out_coffset & 3)) return HEAL_ERR_UNSUPPORTED;
+    if ((out->cstride & 3) || (out->coffset & 3)) return HEAL_ERR_UNSUPPORTED;
     int cg = Cin / groups;
     if (cg * groups != Cin) return HEAL_ERR_ARG;
     if (cg == 4) return launch_grouped<4, 4, 4>(p, st);

@@ -50,12 +50,12 @@ __device__ __forceinline__ Tap make_tap(const double* __restrict__ th, int oh, i
 }
 
 struct FuseP {
-    const float* feat;     // (n, H, W, C) channels-last, pixel stride cs
+    ActV feat;             // (n, H, W, C) channels-last view (fp32 / bf16 / split-bf16)
     const float* occ;      // (n, H, W) occupancy logits
     const double* theta;   // (n, 2, 3) fp64: affine[b, 0, j]
     const int* crop;       // (n, 4) [h0, h1, w0, w1] window where the score is kept, or nullptr
-    float* out;            // (H, W, C) pixel stride out_cs, channel offset out_co
-    int n, H, W, C, cs, out_cs, out_co, align;
+    ActV out;              // (H, W, C)
+    int n, H, W, C, align;
 };
 
 constexpr int FUSE_PIX = 32;
@@ -117,26 +117,25 @@ k_pyramid_fuse(FuseP p) {
         if (pix >= HW) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < p.n; ++j) {
-            const float* fj = p.feat + (size_t)j * HW * p.cs + ch * 4;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);   // warped feature (bilinear), then weighted
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int off = sTap[lp][j].off[k];
                 if (off >= 0) {
                     float w = sTap[lp][j].w[k];
-                    float4 v = ldg_f4(fj + (size_t)off * p.cs);
+                    float4 v = act_load4(p.feat, (size_t)j * HW + off, ch * 4);
                     a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
                 }
             }
             acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
         }
-        stg_f4(p.out + (size_t)pix * p.out_cs + p.out_co + ch * 4, acc);
+        act_store4(p.out, (size_t)pix, ch * 4, acc);
     }
 }
 
 struct AttP {
-    const float* feat; const double* theta; float* out;
-    int n, H, W, C, cs, out_cs, out_co, align;
+    ActV feat; const double* theta; ActV out;
+    int n, H, W, C, align;
     float inv_sqrt_dim;
 };
 
@@ -151,7 +150,6 @@ k_att_fuse(AttP p) {
     Tap taps[MAX_AGENTS];
     for (int j = 0; j < p.n; ++j) taps[j] = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
     auto sample = [&](int j, float4* x) {
-        const float* fj = p.feat + (size_t)j * HW * p.cs + 4 * lane;
 #pragma unroll
         for (int q = 0; q < Q; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -161,7 +159,7 @@ k_att_fuse(AttP p) {
                 float w = taps[j].w[k];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    float4 v = ldg_f4(fj + (size_t)off * p.cs + 128 * q);
+                    float4 v = act_load4(p.feat, (size_t)j * HW + off, 4 * lane + 128 * q);
                     x[q].x = fmaf(v.x, w, x[q].x); x[q].y = fmaf(v.y, w, x[q].y);
                     x[q].z = fmaf(v.z, w, x[q].z); x[q].w = fmaf(v.w, w, x[q].w);
                 }
@@ -202,34 +200,38 @@ k_att_fuse(AttP p) {
         }
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) stg_f4(p.out + (size_t)pix * p.out_cs + p.out_co + 4 * lane + 128 * q, acc[q]);
+    for (int q = 0; q < Q; ++q) act_store4(p.out, (size_t)pix, 4 * lane + 128 * q, acc[q]);
 }
 
 }  // namespace
 
-extern "C" int heal_pyramid_fuse_level(const float* feat, int feat_cstride, const float* occ, const double* theta,
+static inline ActV to_view(const heal_act_t* a) {
+    ActV v;
+    v.p = a->data; v.fmt = a->fmt; v.cs = a->cstride; v.co = a->coffset; v.plane = a->plane_stride;
+    return v;
+}
+
+extern "C" int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ, const double* theta,
                                        const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
-                                       float* out, int out_cstride, int out_coffset, void* stream_) {
-    if (!feat || !occ || !theta || !out) return HEAL_ERR_ARG;
+                                       const heal_act_t* out, void* stream_) {
+    if (!feat || !feat->data || !occ || !theta || !out || !out->data) return HEAL_ERR_ARG;
     if (n_agents < 1 || n_agents > MAX_AGENTS) return HEAL_ERR_UNSUPPORTED;
-    if ((C & 3) || (feat_cstride & 3) || (out_cstride & 3) || (out_coffset & 3)) return HEAL_ERR_UNSUPPORTED;
+    if ((C & 3) || (feat->cstride & 3) || (feat->coffset & 3) || (out->cstride & 3) || (out->coffset & 3)) return HEAL_ERR_UNSUPPORTED;
     FuseP p;
-    p.feat = feat; p.occ = occ; p.theta = theta; p.crop = crop_windows; p.out = out;
-    p.n = n_agents; p.H = H; p.W = W; p.C = C; p.cs = feat_cstride; p.out_cs = out_cstride; p.out_co = out_coffset;
-    p.align = align_corners;
+    p.feat = to_view(feat); p.occ = occ; p.theta = theta; p.crop = crop_windows; p.out = to_view(out);
+    p.n = n_agents; p.H = H; p.W = W; p.C = C; p.align = align_corners;
     int grid = (H * W + FUSE_PIX - 1) / FUSE_PIX;
     k_pyramid_fuse<<<grid, 256, 0, (cudaStream_t)stream_>>>(p);
     return heal_check_launch();
 }
 
-extern "C" int heal_att_fuse(const float* feat, int feat_cstride, const double* theta, int n_agents, int H, int W, int C,
-                             float* out, int out_cstride, int out_coffset, void* stream_) {
-    if (!feat || !theta || !out) return HEAL_ERR_ARG;
+extern "C" int heal_att_fuse(const heal_act_t* feat, const double* theta, int n_agents, int H, int W, int C,
+                             const heal_act_t* out, void* stream_) {
+    if (!feat || !feat->data || !theta || !out || !out->data) return HEAL_ERR_ARG;
     if (n_agents < 1 || n_agents > MAX_AGENTS) return HEAL_ERR_UNSUPPORTED;
-    if ((C % 128) || C > 512 || (feat_cstride & 3) || (out_cstride & 3) || (out_coffset & 3)) return HEAL_ERR_UNSUPPORTED;
+    if ((C % 128) || C > 512 || (feat->cstride & 3) || (feat->coffset & 3) || (out->cstride & 3) || (out->coffset & 3)) return HEAL_ERR_UNSUPPORTED;
     AttP p;
-    p.feat = feat; p.theta = theta; p.out = out; p.n = n_agents; p.H = H; p.W = W; p.C = C; p.cs = feat_cstride;
-    p.out_cs = out_cstride; p.out_co = out_coffset; p.align = 0;
+    p.feat = to_view(feat); p.theta = theta; p.out = to_view(out); p.n = n_agents; p.H = H; p.W = W; p.C = C; p.align = 0;
     p.inv_sqrt_dim = 1.0f / sqrtf((float)C);
     int grid = (H * W + 7) / 8;
     cudaStream_t st = (cudaStream_t)stream_;

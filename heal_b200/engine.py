@@ -1,9 +1,16 @@
-"""Execution helpers shared by the mirror modules: parameter folding/packing cache and conv runners.
+"""Execution helpers shared by the mirror modules: precision mode, parameter folding/packing cache and
+the conv dispatcher (tcgen05 implicit GEMM where eligible, fp32 CUDA-core kernel otherwise).
 
 Parameters stay ordinary nn.Parameters with the reference's state-dict key names
 (SURVEY.md 8b "Parameters / ownership"); what the kernels consume is a *derived* cache (BN folded in
 fp64, weights re-laid out for the kernels) that is rebuilt whenever a source tensor's version counter
 changes (load_state_dict / optimizer step) or the module moves device.
+
+Precision modes (set_precision):
+  'tc32'  (default) dense stride-1 convs on tcgen05 with split-bf16 operands (3 MMAs / K-step, fp32
+          accumulate: fp32-equivalent, meets the 1e-3 parity bar); activations stored as split-bf16.
+  'bf16'  same kernels with a single bf16 plane (1e-2 parity bar, BASELINE config 4).
+  'fp32'  everything on the fp32 CUDA-core kernels with fp32 storage (exact-fp32 cross-check path).
 """
 from __future__ import annotations
 
@@ -14,6 +21,20 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .ops import Act
+
+PRECISION = "tc32"
+
+
+def set_precision(mode: str):
+    global PRECISION
+    assert mode in ("tc32", "bf16", "fp32")
+    PRECISION = mode
+
+
+def act_fmt() -> str:
+    return {"tc32": "split", "bf16": "bf16", "fp32": "f32"}[PRECISION]
+
 
 _CACHE = weakref.WeakKeyDictionary()
 
@@ -29,18 +50,19 @@ def _sig(*mods):
     return tuple(sig)
 
 
-def packed(conv: nn.Module, bn: Optional[nn.Module], relu: bool, extra_pad: int = 0) -> ops.PackedConv:
-    """Folded + packed weights for `conv` (+ eval `bn`) on conv.weight's device, cached."""
+def packed(conv: nn.Module, bn: Optional[nn.Module], relu: bool, extra_pad: int = 0, kind: str = "simt"):
+    """Folded + packed weights for `conv` (+ eval `bn`) on conv.weight's device, cached per (module, kind)."""
     sig = (_sig(conv, bn), relu, extra_pad)
-    hit = _CACHE.get(conv)
+    slot = _CACHE.setdefault(conv, {})
+    hit = slot.get(kind)
     if hit is not None and hit[0] == sig:
         return hit[1]
-    if isinstance(conv, nn.ConvTranspose2d):
-        pc = ops.pack_deconv(conv, bn, relu)
+    if kind == "simt":
+        pc = ops.pack_deconv(conv, bn, relu) if isinstance(conv, nn.ConvTranspose2d) else ops.pack_conv(conv, bn, relu, extra_pad)
     else:
-        pc = ops.pack_conv(conv, bn, relu, extra_pad)
+        pc = ops.pack_conv_tc(conv, bn, relu, planes=2 if kind == "tc2" else 1, extra_pad=extra_pad)
     pc.to(conv.weight.device)
-    _CACHE[conv] = (sig, pc)
+    slot[kind] = (sig, pc)
     return pc
 
 
@@ -51,6 +73,26 @@ def require_eval(module: nn.Module):
             "(model.eval(), torch.no_grad()); autograd through them is a 'next' row (SURVEY.md 8f-4).")
 
 
-def conv_bn_act(x, conv, bn=None, relu=False, residual=None, out=None, out_coffset=0, extra_pad=0):
-    """x / residual / out: NHWC buffers.  conv(+bn)(+residual)(+relu) in one kernel."""
-    return ops.conv2d(x, packed(conv, bn, relu, extra_pad), residual=residual, out=out, out_coffset=out_coffset)
+def conv_bn_act(x: Act, conv, bn=None, relu=False, residual: Optional[Act] = None, out: Optional[Act] = None,
+                out_coffset: int = 0, extra_pad: int = 0, out_fmt: Optional[str] = None) -> Act:
+    """conv(+bn)(+residual)(+relu) as ONE kernel.  `out_fmt` defaults to the mode's activation format;
+    pass 'f32' for tensors that leave the conv engine (occupancy logits, prediction heads)."""
+    fmt = act_fmt()
+    if out is not None:
+        out_fmt = out.fmt
+    elif out_fmt is None:
+        out_fmt = fmt
+    if PRECISION != "fp32" and ops.tc_eligible(conv):
+        if x.fmt != fmt:
+            x = ops.convert(x, fmt)
+        if residual is not None and residual.fmt not in ("f32", fmt):
+            residual = ops.convert(residual, fmt)
+        pc = packed(conv, bn, relu, extra_pad, kind="tc2" if PRECISION == "tc32" else "tc1")
+        if out_fmt == "f32":
+            _, o32 = ops.conv2d_tc(x, pc, residual=residual, want_split=False, out_f32=out, want_f32=True,
+                                   out32_coffset=out_coffset)
+            return o32
+        o, _ = ops.conv2d_tc(x, pc, residual=residual, out=out, out_coffset=out_coffset)
+        return o
+    pc = packed(conv, bn, relu, extra_pad, kind="simt")
+    return ops.conv2d_simt(x, pc, residual=residual, out=out, out_fmt=out_fmt, out_coffset=out_coffset)

@@ -1,5 +1,5 @@
-"""AttFusion / MaxFusion mirror (opencood/models/fuse_modules/fusion_in_one.py:87-151): same
-`forward(x, record_len, affine_matrix)` signature.  The other six fusion operators of that file are
+"""AttFusion mirror (opencood/models/fuse_modules/fusion_in_one.py:126-151): same
+`forward(x, record_len, affine_matrix)` signature.  The other fusion operators of that file are
 out of the hot-path scope."""
 import numpy as np
 import torch
@@ -33,15 +33,15 @@ class AttFusion(nn.Module):
         self.feature_dims = feature_dims
 
     def forward_nhwc(self, x, record_len, affine_matrix):
+        """x: Act (sumN,H,W,C) -> Act (B,H,W,C)"""
         rl = _rl(record_len)
-        _, H, W, C = x.shape
-        out = torch.empty((len(rl), H, W, C), dtype=torch.float32, device=x.device)
+        out = ops.act_empty(len(rl), x.H, x.W, x.C, x.fmt, x.device)
         aff = affine_matrix.to(device=x.device, dtype=torch.float64)
         start = 0
         for b, n in enumerate(rl):
-            ops.att_fuse(x[start:start + n], aff[b, 0, :n].contiguous(), out=out[b])
+            ops.att_fuse(x.images(start, start + n), aff[b, 0, :n].contiguous(), out=out.image(b))
             start += n
         return out
 
     def forward(self, xx, record_len, affine_matrix):
-        return ops.from_nhwc(self.forward_nhwc(ops.to_nhwc(xx), record_len, affine_matrix))
+        return ops.act_to_nchw(self.forward_nhwc(ops.to_act(xx), record_len, affine_matrix))

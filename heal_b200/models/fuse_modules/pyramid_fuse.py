@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import conv_bn_act, require_eval
+from ...engine import conv_bn_act, require_eval, act_fmt
 from ..sub_modules.base_bev_backbone_resnet import ResNetBEVBackbone
 from ..sub_modules.resblock import ResNetModified, Bottleneck
 
@@ -18,21 +18,19 @@ def _record_len_list(record_len):
     return [int(v) for v in record_len]
 
 
-def weighted_fuse_nhwc(x, occ, record_len, affine_matrix, align_corners, crop_windows=None, out=None):
-    """x (sumN,H,W,C) NHWC buffer, occ (sumN,H,W) logits, affine (B,L,L,2,3) f64 -> (B,H,W,C).
+def weighted_fuse_nhwc(x, occ, record_len, affine_matrix, align_corners, crop_windows=None):
+    """x: Act (sumN,H,W,C); occ (sumN,H,W) f32 logits; affine (B,L,L,2,3) f64 -> Act (B,H,W,C).
     Same contract as weighted_fuse (pyramid_fuse.py:17-63), with score = sigmoid(occ)+1e-4 and the
     crop mask folded in (pyramid_fuse.py:145-162)."""
     rl = _record_len_list(record_len)
     B = len(rl)
-    _, H, W, C = x.shape
-    if out is None:
-        out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    out = ops.act_empty(B, x.H, x.W, x.C, x.fmt, x.device)
     aff = affine_matrix.to(device=x.device, dtype=torch.float64)
     start = 0
     for b, n in enumerate(rl):
         theta = aff[b, 0, :n].contiguous()
         cw = crop_windows[start:start + n] if crop_windows is not None else None
-        ops.pyramid_fuse_level(x[start:start + n], occ[start:start + n], theta, align_corners, cw, out=out[b])
+        ops.pyramid_fuse_level(x.images(start, start + n), occ[start:start + n], theta, align_corners, cw, out=out.image(b))
         start += n
     return out
 
@@ -50,32 +48,34 @@ class PyramidFusion(ResNetBEVBackbone):
             setattr(self, f"single_head_{i}", nn.Conv2d(model_cfg["num_filters"][i], 1, kernel_size=1))
 
     def _occ_nhwc(self, feat, i):
-        return conv_bn_act(feat, getattr(self, f"single_head_{i}"), None, relu=False)   # (N,H,W,1)
+        return conv_bn_act(feat, getattr(self, f"single_head_{i}"), None, relu=False, out_fmt="f32")   # Act f32 (N,H,W,1)
 
     def forward_single(self, spatial_features):
         require_eval(self)
-        feats = self.multiscale_nhwc(ops.to_nhwc(spatial_features))
-        occ = [ops.from_nhwc(self._occ_nhwc(f, i)) for i, f in enumerate(feats)]
-        return ops.from_nhwc(self.decode_nhwc(feats)), occ
+        feats = self.multiscale_nhwc(ops.to_act(spatial_features))
+        occ = [ops.act_to_nchw(self._occ_nhwc(f, i)) for i, f in enumerate(feats)]
+        return ops.act_to_nchw(self.decode_nhwc(feats)), occ
 
     def _crop_windows(self, H, W, agent_modality_list, cam_crop_info, device):
         """(sumN,4) int32 [h0,h1,w0,w1] per agent: region where the score survives (pyramid_fuse.py:147-162)."""
+        def clamp(s, e, n):   # python slice semantics of [s:e] on a length-n axis
+            s = max(n + s, 0) if s < 0 else min(s, n)
+            e = max(n + e, 0) if e < 0 else min(e, n)
+            return s, max(e, s)
         win = []
         for m in agent_modality_list:
             if m in cam_crop_info:
                 crop_H = H / cam_crop_info[m][f"crop_ratio_H_{m}"] - 4
                 crop_W = W / cam_crop_info[m][f"crop_ratio_W_{m}"] - 4
-                sh, eh = int(H // 2 - crop_H // 2), int(H // 2 + crop_H // 2)
-                sw, ew = int(W // 2 - crop_W // 2), int(W // 2 + crop_W // 2)
-                # python slicing semantics of [sh:eh, sw:ew]
-                sh, eh = max(sh, 0) if sh >= 0 else max(H + sh, 0), min(eh, H) if eh >= 0 else max(H + eh, 0)
-                sw, ew = max(sw, 0) if sw >= 0 else max(W + sw, 0), min(ew, W) if ew >= 0 else max(W + ew, 0)
+                sh, eh = clamp(int(H // 2 - crop_H // 2), int(H // 2 + crop_H // 2), H)
+                sw, ew = clamp(int(W // 2 - crop_W // 2), int(W // 2 + crop_W // 2), W)
                 win.append([sh, eh, sw, ew])
             else:
                 win.append([0, H, 0, W])
         return torch.tensor(win, dtype=torch.int32, device=device)
 
     def forward_collab_nhwc(self, x, record_len, affine_matrix, agent_modality_list=None, cam_crop_info=None):
+        """x: Act (sumN,H,W,C) -> (fused Act (B,H,W,sum C_up), [occ Act f32 (sumN,h,w,1)] per level)."""
         require_eval(self)
         feats = self.multiscale_nhwc(x)
         crop = cam_crop_info is not None and len(cam_crop_info) > 0
@@ -85,12 +85,11 @@ class PyramidFusion(ResNetBEVBackbone):
             occs.append(occ)
             cw = None
             if crop and not self.training:
-                cw = self._crop_windows(f.shape[1], f.shape[2], agent_modality_list, cam_crop_info, f.device)
-            fused.append(weighted_fuse_nhwc(f, occ.view(f.shape[0], f.shape[1], f.shape[2]), record_len,
-                                            affine_matrix, self.align_corners, cw))
+                cw = self._crop_windows(f.H, f.W, agent_modality_list, cam_crop_info, f.device)
+            fused.append(weighted_fuse_nhwc(f, occ.t.view(f.N, f.H, f.W), record_len, affine_matrix, self.align_corners, cw))
         return self.decode_nhwc(fused), occs
 
     def forward_collab(self, spatial_features, record_len, affine_matrix, agent_modality_list=None, cam_crop_info=None):
-        fused, occs = self.forward_collab_nhwc(ops.to_nhwc(spatial_features), record_len, affine_matrix,
+        fused, occs = self.forward_collab_nhwc(ops.to_act(spatial_features), record_len, affine_matrix,
                                                agent_modality_list, cam_crop_info)
-        return ops.from_nhwc(fused), [ops.from_nhwc(o) for o in occs]
+        return ops.act_to_nchw(fused), [ops.act_to_nchw(o) for o in occs]

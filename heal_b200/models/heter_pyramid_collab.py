@@ -34,7 +34,7 @@ class FusedHeads:
                 conv.weight.copy_(torch.cat([h.weight for h in self.heads], 0))
                 conv.bias.copy_(torch.cat([h.bias for h in self.heads], 0))
             self._conv, self._sig = conv, sig
-        y = conv_bn_act(x_nhwc, self._conv, None, relu=False)          # (B,H,W,sum)
+        y = conv_bn_act(x_nhwc, self._conv, None, relu=False, out_fmt="f32").t          # (B,H,W,sum) fp32
         outs, o = [], 0
         for h in self.heads:
             outs.append(y[..., o:o + h.out_channels].permute(0, 3, 1, 2).contiguous())
@@ -87,9 +87,15 @@ class HeterPyramidCollab(nn.Module):
         pass
 
     @staticmethod
-    def _center_crop_nhwc(f, th, tw):
-        """torchvision CenterCrop semantics on an NHWC buffer: crops, or zero-pads when the target is larger
-        (heter_pyramid_collab.py:153-163)."""
+    def _center_crop_nhwc(act, th, tw):
+        """torchvision CenterCrop semantics on a channels-last map: crops, or zero-pads when the target is larger
+        (heter_pyramid_collab.py:153-163).  Layout plumbing on the fp32 view."""
+        f = ops.convert(act, "f32").t
+        f = HeterPyramidCollab._crop_tensor(f, th, tw)
+        return ops.Act(f, "f32")
+
+    @staticmethod
+    def _crop_tensor(f, th, tw):
         n, h, w, c = f.shape
         if th > h or tw > w:
             pl, pt = (tw - w) // 2 if tw > w else 0, (th - h) // 2 if th > h else 0
@@ -114,12 +120,11 @@ class HeterPyramidCollab(nn.Module):
                 continue
             f = getattr(self, f"encoder_{m}")(data_dict, m)                       # logical NCHW, physical NHWC
             bb = getattr(self, f"backbone_{m}")
-            f = bb.decode_nhwc(bb.multiscale_nhwc(ops.to_nhwc(f)))
-            f = ops.to_nhwc(getattr(self, f"aligner_{m}")(ops.from_nhwc(f)))
+            f = bb.decode_nhwc(bb.multiscale_nhwc(ops.to_act(f)))                 # Act
+            # aligner_m is the identity for every in-scope modality (AlignNet raises otherwise)
             if self.sensor_type_dict[m] == "camera":
-                _, H, W, _ = f.shape
-                f = self._center_crop_nhwc(f, int(H * getattr(self, f"crop_ratio_H_{m}")),
-                                           int(W * getattr(self, f"crop_ratio_W_{m}")))
+                f = self._center_crop_nhwc(f, int(f.H * getattr(self, f"crop_ratio_H_{m}")),
+                                           int(f.W * getattr(self, f"crop_ratio_W_{m}")))
                 if getattr(self, f"depth_supervision_{m}"):
                     output_dict[f"depth_items_{m}"] = getattr(self, f"encoder_{m}").depth_items
             feats[m] = f
@@ -129,13 +134,13 @@ class HeterPyramidCollab(nn.Module):
             cnt = {m: 0 for m in self.modality_name_list}
             rows = []
             for m in aml:
-                rows.append(feats[m][cnt[m]])
+                rows.append(ops.convert(feats[m].image(cnt[m]), "f32").t)
                 cnt[m] += 1
-            x = torch.stack(rows)
+            x = ops.Act(torch.cat(rows, 0), "f32")
         fused, occs = self.pyramid_backbone.forward_collab_nhwc(x, record_len, affine, aml, self.cam_crop_info)
         if self.shrink_flag:
             fused = self.shrink_conv.forward_nhwc(fused)
         cls, reg, dirp = self._heads(fused)
         output_dict.update({'cls_preds': cls, 'reg_preds': reg, 'dir_preds': dirp})
-        output_dict['occ_single_list'] = [ops.from_nhwc(o) for o in occs]
+        output_dict['occ_single_list'] = [ops.act_to_nchw(o) for o in occs]
         return output_dict

@@ -5,6 +5,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...engine import conv_bn_act, require_eval
+from .base_bev_backbone_resnet import decode_levels
 
 
 class BaseBEVBackbone(nn.Module):
@@ -59,25 +60,16 @@ class BaseBEVBackbone(nn.Module):
         return feats
 
     def decode_nhwc(self, feats):
-        couts = [d[0].out_channels for d in self.deblocks]
-        s0 = self.deblocks[0][0].stride[0] if isinstance(self.deblocks[0][0], nn.ConvTranspose2d) else 1
-        N, H0, W0, _ = feats[0].shape
-        out = torch.empty((N, H0 * s0, W0 * s0, sum(couts)), dtype=torch.float32, device=feats[0].device)
-        off = 0
-        for f, d, c in zip(feats, self.deblocks, couts):
-            conv_bn_act(f, d[0], d[1], relu=True, out=out, out_coffset=off)
-            off += c
-        return out
+        return decode_levels(self.deblocks, feats)
 
     def forward(self, data_dict):
         require_eval(self)
-        x = ops.to_nhwc(data_dict['spatial_features'])
-        feats = self.multiscale_nhwc(x)
-        data_dict['spatial_features_2d'] = ops.from_nhwc(self.decode_nhwc(feats))
+        feats = self.multiscale_nhwc(ops.to_act(data_dict['spatial_features']))
+        data_dict['spatial_features_2d'] = ops.act_to_nchw(self.decode_nhwc(feats))
         return data_dict
 
     def get_multiscale_feature(self, spatial_features):
-        return [ops.from_nhwc(f) for f in self.multiscale_nhwc(ops.to_nhwc(spatial_features))]
+        return [ops.act_to_nchw(f) for f in self.multiscale_nhwc(ops.to_act(spatial_features))]
 
     def decode_multiscale_feature(self, x):
-        return ops.from_nhwc(self.decode_nhwc([ops.to_nhwc(f) for f in x]))
+        return ops.act_to_nchw(self.decode_nhwc([ops.to_act(f) for f in x]))

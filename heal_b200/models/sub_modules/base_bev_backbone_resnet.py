@@ -4,8 +4,29 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import conv_bn_act, require_eval
+from ...engine import conv_bn_act, require_eval, act_fmt
 from .resblock import ResNetModified, BasicBlock
+
+
+def decode_levels(deblocks, feats):
+    """deblocks (ConvTranspose2d k==s | Conv2d k==s, + BN + ReLU) with the channel concat written in place
+    into one (N,H,W,sum C) buffer (base_bev_backbone_resnet.py:127-142 / base_bev_backbone.py:139-156)."""
+    if len(deblocks) == 0:
+        if len(feats) == 1:
+            return feats[0]
+        raise NotImplementedError("multi-level backbone without deblocks is not used by any HEAL yaml")
+    couts = [d[0].out_channels for d in deblocks]
+    d0 = deblocks[0][0]
+    if isinstance(d0, nn.ConvTranspose2d):
+        H0, W0 = feats[0].H * d0.stride[0], feats[0].W * d0.stride[0]
+    else:
+        H0, W0 = feats[0].H // d0.stride[0], feats[0].W // d0.stride[0]
+    out = ops.act_empty(feats[0].N, H0, W0, sum(couts), act_fmt(), feats[0].device)
+    off = 0
+    for f, d, c in zip(feats, deblocks, couts):
+        conv_bn_act(f, d[0], d[1], relu=True, out=out, out_coffset=off)
+        off += c
+    return out
 
 
 class ResNetBEVBackbone(nn.Module):
@@ -40,42 +61,30 @@ class ResNetBEVBackbone(nn.Module):
             raise NotImplementedError("extra trailing deblock (upsample_strides longer than levels) is not used by any HEAL yaml")
         self.num_bev_features = c_in
 
-    # ---- NHWC internals ------------------------------------------------------------------------
+    # ---- channels-last internals (Act in / Act out) ---------------------------------------------
     def multiscale_nhwc(self, x):
         return self.resnet.forward_nhwc(x)
 
     def decode_nhwc(self, feats):
-        """deblocks + channel concat written in place into one (N,H,W,sum C) buffer."""
-        if len(self.deblocks) == 0:
-            return feats[0] if len(feats) == 1 else torch.cat(feats, dim=3)
-        couts = [d[0].out_channels for d in self.deblocks]
-        ups = [d[0].stride[0] if isinstance(d[0], nn.ConvTranspose2d) else None for d in self.deblocks]
-        N, H0, W0, _ = feats[0].shape
-        s0 = ups[0] if ups[0] is not None else 1
-        out = torch.empty((N, H0 * s0, W0 * s0, sum(couts)), dtype=torch.float32, device=feats[0].device)
-        off = 0
-        for f, d, c in zip(feats, self.deblocks, couts):
-            conv_bn_act(f, d[0], d[1], relu=True, out=out, out_coffset=off)
-            off += c
-        return out
+        return decode_levels(self.deblocks, feats)
 
     # ---- reference API --------------------------------------------------------------------------
     def forward(self, data_dict):
         require_eval(self)
-        feats = self.multiscale_nhwc(ops.to_nhwc(data_dict['spatial_features']))
-        data_dict['spatial_features_2d'] = ops.from_nhwc(self.decode_nhwc(feats))
+        feats = self.multiscale_nhwc(ops.to_act(data_dict['spatial_features']))
+        data_dict['spatial_features_2d'] = ops.act_to_nchw(self.decode_nhwc(feats))
         return data_dict
 
     def get_multiscale_feature(self, spatial_features):
         require_eval(self)
-        return [ops.from_nhwc(f) for f in self.multiscale_nhwc(ops.to_nhwc(spatial_features))]
+        return [ops.act_to_nchw(f) for f in self.multiscale_nhwc(ops.to_act(spatial_features))]
 
     def decode_multiscale_feature(self, x):
         require_eval(self)
-        return ops.from_nhwc(self.decode_nhwc([ops.to_nhwc(f) for f in x]))
+        return ops.act_to_nchw(self.decode_nhwc([ops.to_act(f) for f in x]))
 
     def get_layer_i_feature(self, spatial_features, layer_i):
-        x = ops.to_nhwc(spatial_features)
+        x = ops.to_act(spatial_features)
         for blk in getattr(self.resnet, f"layer{layer_i}"):
             x = blk.forward_nhwc(x)
-        return ops.from_nhwc(x)
+        return ops.act_to_nchw(x)

@@ -19,7 +19,7 @@ class DoubleConv(nn.Module):
         return conv_bn_act(x, self.double_conv[2], None, relu=True)
 
     def forward(self, x):
-        return ops.from_nhwc(self.forward_nhwc(ops.to_nhwc(x)))
+        return ops.act_to_nchw(self.forward_nhwc(ops.to_act(x)))
 
 
 class DownsampleConv(nn.Module):
@@ -37,4 +37,4 @@ class DownsampleConv(nn.Module):
         return x
 
     def forward(self, x):
-        return ops.from_nhwc(self.forward_nhwc(ops.to_nhwc(x)))
+        return ops.act_to_nchw(self.forward_nhwc(ops.to_act(x)))

@@ -1,11 +1,12 @@
 """ResNet / ResNeXt blocks mirror (opencood/models/sub_modules/resblock.py:18-219).
 
 nn.Conv2d / nn.BatchNorm2d modules are kept only as parameter containers with the reference's
-state-dict names; forward runs each conv+BN(+residual)+ReLU as ONE kernel on NHWC buffers."""
-from typing import List, Optional
+state-dict names; forward runs each conv+BN(+residual)+ReLU as ONE kernel on channels-last `Act`s."""
+from typing import List
 
 import torch.nn as nn
 
+from ... import ops
 from ...engine import conv_bn_act
 
 
@@ -103,5 +104,4 @@ class ResNetModified(nn.Module):
         return feats
 
     def forward(self, x):
-        from ... import ops
-        return [ops.from_nhwc(f) for f in self.forward_nhwc(ops.to_nhwc(x))]
+        return [ops.act_to_nchw(f) for f in self.forward_nhwc(ops.to_act(x))]

@@ -4,22 +4,24 @@ PyTorch is used here only for device memory, streams and shapes: every wrapper p
 pointers + the current CUDA stream to libheal_b200.so.  There is no eager / CPU fallback: a tensor
 that is not on a CUDA device raises.
 
-Layout convention: feature maps are exchanged as *logically* (N,C,H,W) torch tensors that are
-*physically* channels-last, i.e. `x.permute(0,2,3,1)` is a contiguous (N,H,W,C) buffer.  This keeps
-the reference's tensor shapes at every module boundary at zero cost.
+Activations travel between kernels as `Act` objects: channels-last buffers in one of three storage
+formats — 'f32' (N,H,W,C) fp32; 'bf16' (1,N,H,W,C) bf16; 'split' (2,N,H,W,C) bf16 planes (hi, lo) with
+x ~= hi + lo (16 mantissa bits), the operand format of the tcgen05 fp32-equivalent convolution.
+At module boundaries feature maps are *logically* (N,C,H,W) fp32 torch tensors that are *physically*
+channels-last (`x.permute(0,2,3,1)` contiguous), which keeps the reference's shapes at zero cost.
 """
 from __future__ import annotations
 
 import ctypes
-import math
 from typing import Optional, Sequence
 
 import numpy as np
 import torch
 
-from ._lib import lib, check
+from ._lib import lib, check, HealAct
 
 _vp = ctypes.c_void_p
+FMT = {"f32": 0, "bf16": 1, "split": 2}
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -37,8 +39,7 @@ def _need_cuda(*ts):
 
 
 def _host_f32(vals: Sequence[float]):
-    arr = (ctypes.c_float * len(vals))(*[float(np.float32(v)) for v in vals])
-    return arr
+    return (ctypes.c_float * len(vals))(*[float(np.float32(v)) for v in vals])
 
 
 def _host_i32(vals: Sequence[int]):
@@ -48,12 +49,12 @@ def _host_i32(vals: Sequence[int]):
 _WS = {}
 
 # bench.py instrumentation: when PROFILE is a list, every wrapper brackets its C-ABI call with CUDA events
-# on the launching stream and appends (kernel family, algorithmic flops-or-bytes, start, end).
+# on the launching stream and appends (kernel family, algorithmic flops, start, end).
 PROFILE = None
 
 
 class _Prof:
-    def __init__(self, name, work):
+    def __init__(self, name, work=0.0):
         self.name, self.work = name, work
 
     def __enter__(self):
@@ -80,8 +81,62 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
-# layout helpers
+# activations
 # ------------------------------------------------------------------------------------------------
+class Act:
+    """Channels-last activation buffer.  fmt 'f32': t is (N,H,W,C) fp32; 'bf16'/'split': t is (P,N,H,W,C) bf16."""
+
+    def __init__(self, t: torch.Tensor, fmt: str):
+        _need_cuda(t)
+        self.t, self.fmt = t, fmt
+        if fmt == "f32":
+            assert t.dtype == torch.float32 and t.dim() == 4
+            n, h, w, c = t.shape
+            sn, sh, sw, sc = t.stride()
+            self.plane_stride = 0
+        else:
+            assert t.dtype == torch.bfloat16 and t.dim() == 5 and t.shape[0] == (2 if fmt == "split" else 1)
+            _, n, h, w, c = t.shape
+            sp, sn, sh, sw, sc = t.stride()
+            self.plane_stride = sp
+        assert sc == 1 and sh == w * sw and (n == 1 or sn == h * sh), "Act needs a channels-last dense pixel grid"
+        self.N, self.H, self.W, self.C, self.cstride = n, h, w, c, sw
+
+    @property
+    def planes(self):
+        return {"f32": 0, "bf16": 1, "split": 2}[self.fmt]
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def view(self, coffset: int = 0) -> HealAct:
+        return HealAct(self.t.data_ptr(), FMT[self.fmt], self.cstride, coffset, self.plane_stride)
+
+    def images(self, a: int, b: int) -> "Act":
+        return Act(self.t[a:b] if self.fmt == "f32" else self.t[:, a:b], self.fmt)
+
+    def image(self, b: int) -> "Act":
+        return self.images(b, b + 1)
+
+
+def act_empty(N, H, W, C, fmt: str, device) -> Act:
+    if fmt == "f32":
+        return Act(torch.empty((N, H, W, C), dtype=torch.float32, device=device), fmt)
+    return Act(torch.empty((2 if fmt == "split" else 1, N, H, W, C), dtype=torch.bfloat16, device=device), fmt)
+
+
+def convert(a: Act, fmt: str) -> Act:
+    if a.fmt == fmt:
+        return a
+    out = act_empty(a.N, a.H, a.W, a.C, fmt, a.device)
+    sv, dv = a.view(), out.view()
+    with _Prof("act_convert"):
+        rc = lib.heal_act_convert(ctypes.byref(sv), ctypes.byref(dv), a.N * a.H * a.W, a.C, _stream())
+    check(rc, "heal_act_convert")
+    return out
+
+
 def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """(N,C,H,W) logical tensor -> contiguous (N,H,W,C) buffer (view if already channels-last)."""
     assert x.dim() == 4
@@ -92,6 +147,30 @@ def to_nhwc(x: torch.Tensor) -> torch.Tensor:
 def from_nhwc(buf: torch.Tensor) -> torch.Tensor:
     """contiguous (N,H,W,C) buffer -> logical (N,C,H,W) view (channels-last strides)."""
     return buf.permute(0, 3, 1, 2)
+
+
+def to_act(x: torch.Tensor) -> Act:
+    """logical (N,C,H,W) fp32 tensor -> Act('f32')."""
+    _need_cuda(x)
+    return Act(to_nhwc(x.float()), "f32")
+
+
+def act_to_nchw(a: Act) -> torch.Tensor:
+    """Act -> logical (N,C,H,W) fp32 tensor (channels-last strides)."""
+    return from_nhwc(convert(a, "f32").t)
+
+
+def split_bf16(x: torch.Tensor, planes: int = 2) -> torch.Tensor:
+    """fp32 (...) -> bf16 (planes, ...) with hi = bf16(x), lo = bf16(x - hi)  (host-side packing / test helper)."""
+    hi = x.to(torch.bfloat16)
+    if planes == 1:
+        return hi.unsqueeze(0).contiguous()
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def merge_bf16(s: torch.Tensor) -> torch.Tensor:
+    return s.float().sum(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -125,7 +204,7 @@ def voxelize(points: torch.Tensor, agent_offsets: torch.Tensor, lidar_range, vox
     nvox = torch.zeros((1 + A,), dtype=torch.int32, device=dev)
     ws_bytes = lib.heal_voxelize_workspace(P, cap, A)
     ws = _workspace(dev, ws_bytes)
-    with _Prof("voxelize", 0):
+    with _Prof("voxelize"):
         rc = lib.heal_voxelize(_p(points), _p(agent_offsets), A, P,
                                _host_f32(lidar_range[0:3]), _host_f32(voxel_size), _host_i32(grid),
                                T, int(max_voxels), cap, _p(voxels), _p(coords), _p(npts), _p(nvox),
@@ -165,7 +244,7 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
                        voxel_size, lidar_range, nx: int, ny: int, batch_size: int,
                        want_pillar_features: bool = False, want_canvas: bool = True,
                        num_voxels_dev: Optional[torch.Tensor] = None):
-    """Returns (pillar_features (M,64) | None, canvas logical (B,64,ny,nx) channels-last | None)."""
+    """Returns (pillar_features (M,64) | None, canvas logical (B,64,ny,nx) channels-last fp32 | None)."""
     _need_cuda(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded)
     M, T, C = voxel_features.shape
     assert C == 4
@@ -177,7 +256,7 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
     pf = torch.empty((M, cout), dtype=torch.float32, device=dev) if want_pillar_features else None
     vs = [float(v) for v in voxel_size]
     off = [vs[i] / 2 + float(lidar_range[i]) for i in range(3)]
-    with _Prof("pillar_vfe_scatter(+canvas memset)", 0):
+    with _Prof("pillar_vfe_scatter(+canvas memset)"):
         canvas = torch.zeros((batch_size, ny, nx, cout), dtype=torch.float32, device=dev) if want_canvas else None
         rc = lib.heal_pillar_vfe_scatter(_p(vf), _p(npts), _p(coords), _p(num_voxels_dev), M, T,
                                          _p(w_folded), _p(b_folded), w_folded.shape[0], cout,
@@ -187,10 +266,18 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
 
 
 # ------------------------------------------------------------------------------------------------
-# conv2d (fp32 CUDA-core path)
+# conv2d: parameter folding / packing
 # ------------------------------------------------------------------------------------------------
+def _bn_scale_shift(bn, cout):
+    if bn is None:
+        return torch.ones(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64)
+    scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+    shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+    return scale, shift
+
+
 class PackedConv:
-    """Host-side folded + packed parameters of one Conv2d(+BN)(+ReLU) for the C ABI."""
+    """Folded + packed parameters of one Conv2d(+BN)(+ReLU) for heal_conv2d_simt (fp32 CUDA-core path)."""
 
     def __init__(self, weight, bias, kh, kw, stride, pad, groups, cin, cout, relu, w_cstride, deconv_up=1):
         self.weight, self.bias = weight, bias
@@ -203,16 +290,8 @@ class PackedConv:
         return self
 
 
-def _bn_scale_shift(bn, cout):
-    if bn is None:
-        return torch.ones(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64)
-    scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
-    shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
-    return scale, shift
-
-
 def pack_conv(conv: torch.nn.Conv2d, bn: Optional[torch.nn.Module], relu: bool, extra_pad: int = 0) -> PackedConv:
-    """Fold eval-mode BN into the conv (fp64 on the host) and pack for heal_conv2d_nhwc_f32."""
+    """Fold eval-mode BN into the conv (fp64 on the host) and pack for heal_conv2d_simt."""
     w = conv.weight.detach().double().cpu()            # (Cout, Cin/g, kh, kw)
     cout, cing, kh, kw = w.shape
     g = conv.groups
@@ -231,7 +310,6 @@ def pack_conv(conv: torch.nn.Conv2d, bn: Optional[torch.nn.Module], relu: bool, 
                           cing, cout, relu, cpad)
     cg = cout // g
     assert cing == cg and kh == 3 and kw == 3
-    # [tap][ci][co][G]
     wg = w.view(g, cg, cg, kh * kw)                     # (G, co, ci, tap)
     wp = wg.permute(3, 2, 1, 0).contiguous()            # (tap, ci, co, G)
     return PackedConv(wp.float(), b.float().contiguous(), kh, kw, conv.stride[0], pad, g, cing * g, cout, relu, 0)
@@ -253,94 +331,6 @@ def pack_deconv(deconv: torch.nn.ConvTranspose2d, bn, relu: bool) -> PackedConv:
     return PackedConv(wp.float().contiguous(), b.float().contiguous(), 1, 1, 1, 0, 1, cin, cout, relu, cpad, deconv_up=k)
 
 
-def conv2d(x: torch.Tensor, pc: PackedConv, residual: Optional[torch.Tensor] = None,
-           out: Optional[torch.Tensor] = None, out_coffset: int = 0, in_coffset: int = 0,
-           cin: Optional[int] = None) -> torch.Tensor:
-    """x, residual, out: contiguous (N,H,W,C*) NHWC buffers.  Returns the NHWC output buffer.
-    `out`/`out_coffset` let a conv write a channel slice of a wider (concat) buffer; `in_coffset`/`cin`
-    read a slice."""
-    _need_cuda(x, pc.weight)
-    N, H, W, Cs = x.shape
-    cin = pc.cin if cin is None else cin
-    assert x.is_contiguous() and x.dtype == torch.float32 and cin + in_coffset <= Cs
-    up = pc.deconv_up
-    Ho = (H + 2 * pc.pad - pc.kh) // pc.stride + 1
-    Wo = (W + 2 * pc.pad - pc.kw) // pc.stride + 1
-    if out is None:
-        out = torch.empty((N, Ho * up, Wo * up, pc.cout), dtype=torch.float32, device=x.device)
-    assert out.is_contiguous() and out.shape[0] == N and out.shape[1] == Ho * up and out.shape[2] == Wo * up
-    ocs = out.shape[3]
-    res_cs = 0
-    if residual is not None:
-        assert residual.is_contiguous() and residual.shape[:3] == out.shape[:3]
-        res_cs = residual.shape[3]
-    st = _stream()
-    fam = ("conv_grouped3x3_f32" if pc.groups > 1 else f"conv_dense{pc.kh}x{pc.kw}_f32")
-    flops = 2.0 * N * Ho * Wo * pc.cout * (cin // pc.groups) * pc.kh * pc.kw * up * up
-    with _Prof(fam, flops):
-      for i in range(up):
-        for j in range(up):
-            wptr = pc.weight if up == 1 else pc.weight[i, j]
-            rc = lib.heal_conv2d_nhwc_f32(_p(x), N, H, W, cin, Cs, in_coffset, _p(wptr), pc.w_cstride, _p(pc.bias),
-                                          pc.kh, pc.kw, pc.stride, pc.pad, pc.groups,
-                                          _p(residual), res_cs, 0, _p(out), Ho, Wo, pc.cout, ocs, out_coffset,
-                                          up, i, j, 1 if pc.relu else 0, st)
-            check(rc, "heal_conv2d_nhwc_f32")
-    return out
-
-
-# ------------------------------------------------------------------------------------------------
-# fusion
-# ------------------------------------------------------------------------------------------------
-def pyramid_fuse_level(feat: torch.Tensor, occ: torch.Tensor, theta: torch.Tensor, align_corners: bool,
-                       crop_windows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                       out_coffset: int = 0) -> torch.Tensor:
-    """feat (n,H,W,C) NHWC buffer, occ (n,H,W) f32, theta (n,2,3) f64 -> out (H,W,C) (NHWC, one scene)."""
-    _need_cuda(feat, occ, theta)
-    n, H, W, C = feat.shape
-    assert feat.is_contiguous() and occ.is_contiguous() and occ.numel() == n * H * W
-    th = theta.to(torch.float64).contiguous()
-    assert th.shape == (n, 2, 3)
-    if out is None:
-        out = torch.empty((H, W, C), dtype=torch.float32, device=feat.device)
-    ocs = out.shape[-1]
-    cw = crop_windows.to(torch.int32).contiguous() if crop_windows is not None else None
-    with _Prof("pyramid_fuse_level", 0):
-        rc = lib.heal_pyramid_fuse_level(_p(feat), C, _p(occ), _p(th), _p(cw), n, H, W, C, 1 if align_corners else 0,
-                                         _p(out), ocs, out_coffset, _stream())
-    check(rc, "heal_pyramid_fuse_level")
-    return out
-
-
-def att_fuse(feat: torch.Tensor, theta: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """feat (n,H,W,C) NHWC buffer, theta (n,2,3) f64 -> (H,W,C)."""
-    _need_cuda(feat, theta)
-    n, H, W, C = feat.shape
-    assert feat.is_contiguous()
-    th = theta.to(torch.float64).contiguous()
-    if out is None:
-        out = torch.empty((H, W, C), dtype=torch.float32, device=feat.device)
-    rc = lib.heal_att_fuse(_p(feat), C, _p(th), n, H, W, C, _p(out), out.shape[-1], 0, _stream())
-    check(rc, "heal_att_fuse")
-    return out
-
-
-# ------------------------------------------------------------------------------------------------
-# conv2d, tcgen05 tensor-core path (split-bf16 activations)
-# ------------------------------------------------------------------------------------------------
-def split_bf16(x: torch.Tensor, planes: int = 2) -> torch.Tensor:
-    """fp32 (...,) -> bf16 (planes, ...) with hi = bf16(x), lo = bf16(x - hi)  (host-side / test helper)."""
-    hi = x.to(torch.bfloat16)
-    if planes == 1:
-        return hi.unsqueeze(0).contiguous()
-    lo = (x - hi.float()).to(torch.bfloat16)
-    return torch.stack([hi, lo]).contiguous()
-
-
-def merge_bf16(s: torch.Tensor) -> torch.Tensor:
-    return s.float().sum(0)
-
-
 def _coutp(cout: int) -> int:
     for c in (16, 32, 64):
         if cout <= c:
@@ -349,10 +339,13 @@ def _coutp(cout: int) -> int:
 
 
 class PackedConvTC:
+    """Folded + packed split-bf16 parameters for heal_conv2d_tc (tcgen05 path)."""
+
     def __init__(self, w, bias, kh, kw, pad, cin, cout, coutp, relu, up, planes):
         self.w, self.bias = w, bias
         self.kh, self.kw, self.pad, self.cin, self.cout, self.coutp = kh, kw, pad, cin, cout, coutp
         self.relu, self.up, self.planes = relu, up, planes
+        self.stride, self.groups = 1, 1
 
     def to(self, device):
         self.w = self.w.to(device)
@@ -360,13 +353,18 @@ class PackedConvTC:
         return self
 
 
+def tc_eligible(conv) -> bool:
+    if isinstance(conv, torch.nn.ConvTranspose2d):
+        return conv.in_channels % 64 == 0 and conv.groups == 1
+    return conv.groups == 1 and conv.stride == (1, 1) and conv.in_channels % 64 == 0 and conv.dilation == (1, 1)
+
+
 def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> PackedConvTC:
-    """Fold BN (fp64), lay weights out as [plane][tap*coutp + co][Cin] split-bf16 for heal_conv2d_tc."""
-    scale_shift = _bn_scale_shift
+    """Fold BN (fp64), lay weights out as [plane][tap*coutp + co][Cin] (split-)bf16 for heal_conv2d_tc."""
     if isinstance(conv, torch.nn.ConvTranspose2d):
         w = conv.weight.detach().double().cpu()            # (Cin, Cout, k, k)
         cin, cout, k, _ = w.shape
-        scale, shift = scale_shift(bn, cout)
+        scale, shift = _bn_scale_shift(bn, cout)
         b = shift + (conv.bias.detach().double().cpu() * scale if conv.bias is not None else 0)
         w = w * scale[None, :, None, None]
         coutp = _coutp(cout)
@@ -377,7 +375,7 @@ def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> P
     w = conv.weight.detach().double().cpu()                # (Cout, Cin, kh, kw)
     cout, cin, kh, kw = w.shape
     assert conv.groups == 1 and conv.stride == (1, 1)
-    scale, shift = scale_shift(bn, cout)
+    scale, shift = _bn_scale_shift(bn, cout)
     b = shift + (conv.bias.detach().double().cpu() * scale if conv.bias is not None else 0)
     w = w * scale[:, None, None, None]
     coutp = _coutp(cout)
@@ -387,36 +385,109 @@ def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> P
     return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, cin, cout, coutp, relu, 1, planes)
 
 
-def conv2d_tc(x_split: torch.Tensor, pc: PackedConvTC, residual_split: Optional[torch.Tensor] = None,
-              residual_f32: Optional[torch.Tensor] = None, want_split: bool = True, want_f32: bool = False,
-              out_split: Optional[torch.Tensor] = None, out_coffset: int = 0, in_coffset: int = 0,
-              out_f32: Optional[torch.Tensor] = None, out32_coffset: int = 0):
-    """x_split: bf16 (planes,N,H,W,Cs).  Returns (out_split | None, out_f32 | None)."""
-    _need_cuda(x_split, pc.w)
-    P, N, H, W, Cs = x_split.shape
-    assert P == pc.planes and x_split.dtype == torch.bfloat16 and x_split.is_contiguous()
+# ------------------------------------------------------------------------------------------------
+# conv2d launchers
+# ------------------------------------------------------------------------------------------------
+def conv2d_simt(x: Act, pc: PackedConv, residual: Optional[Act] = None, out: Optional[Act] = None,
+                out_fmt: str = "f32", out_coffset: int = 0, in_coffset: int = 0, cin: Optional[int] = None) -> Act:
+    """fp32 CUDA-core conv; any storage format in/out."""
+    _need_cuda(pc.weight)
+    N, H, W = x.N, x.H, x.W
+    cin = pc.cin if cin is None else cin
+    assert cin + in_coffset <= x.C
+    up = pc.deconv_up
+    Ho = (H + 2 * pc.pad - pc.kh) // pc.stride + 1
+    Wo = (W + 2 * pc.pad - pc.kw) // pc.stride + 1
+    if out is None:
+        out = act_empty(N, Ho * up, Wo * up, pc.cout, out_fmt, x.device)
+    assert out.N == N and out.H == Ho * up and out.W == Wo * up
+    if residual is not None:
+        assert (residual.N, residual.H, residual.W) == (out.N, out.H, out.W)
+    xv, ov = x.view(in_coffset), out.view(out_coffset)
+    rv = residual.view() if residual is not None else None
+    st = _stream()
+    fam = ("conv_grouped3x3_simt" if pc.groups > 1 else f"conv_dense{pc.kh}x{pc.kw}_simt")
+    flops = 2.0 * N * Ho * Wo * pc.cout * (cin // pc.groups) * pc.kh * pc.kw * up * up
+    with _Prof(fam, flops):
+        for i in range(up):
+            for j in range(up):
+                wptr = pc.weight if up == 1 else pc.weight[i, j]
+                rc = lib.heal_conv2d_simt(ctypes.byref(xv), N, H, W, cin, _p(wptr), pc.w_cstride, _p(pc.bias),
+                                          pc.kh, pc.kw, pc.stride, pc.pad, pc.groups,
+                                          ctypes.byref(rv) if rv is not None else None, ctypes.byref(ov),
+                                          Ho, Wo, pc.cout, up, i, j, 1 if pc.relu else 0, st)
+                check(rc, "heal_conv2d_simt")
+    return out
+
+
+def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Optional[Act] = None,
+              out_coffset: int = 0, in_coffset: int = 0, want_split: bool = True,
+              out_f32: Optional[Act] = None, want_f32: bool = False, out32_coffset: int = 0):
+    """tcgen05 conv.  x: Act 'split' (planes 2) or 'bf16' (planes 1).  Returns (Act split/bf16 | None, Act f32 | None)."""
+    _need_cuda(pc.w)
+    assert x.planes == pc.planes and x.planes in (1, 2)
+    N, H, W = x.N, x.H, x.W
     up = pc.up
     Ho, Wo = H + 2 * pc.pad - pc.kh + 1, W + 2 * pc.pad - pc.kw + 1
-    dev = x_split.device
-    if want_split and out_split is None:
-        out_split = torch.empty((P, N, Ho * up, Wo * up, pc.cout), dtype=torch.bfloat16, device=dev)
+    if want_split and out is None:
+        out = act_empty(N, Ho * up, Wo * up, pc.cout, x.fmt, x.device)
     if want_f32 and out_f32 is None:
-        out_f32 = torch.empty((N, Ho * up, Wo * up, pc.cout), dtype=torch.float32, device=dev)
-    res_cs = 0
-    res_plane = 0
-    if residual_split is not None:
-        res_cs, res_plane = residual_split.shape[-1], residual_split[0].numel()
-    elif residual_f32 is not None:
-        res_cs = residual_f32.shape[-1]
+        out_f32 = act_empty(N, Ho * up, Wo * up, pc.cout, "f32", x.device)
+    res_split = res_f32 = None
+    res_cs = res_plane = 0
+    if residual is not None:
+        if residual.fmt == "f32":
+            res_f32, res_cs = residual.t, residual.cstride
+        else:
+            assert residual.planes == pc.planes
+            res_split, res_cs, res_plane = residual.t, residual.cstride, residual.plane_stride
     fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "")
     flops = 2.0 * N * Ho * Wo * pc.cout * pc.cin * pc.kh * pc.kw * up * up
     with _Prof(fam, flops):
-        rc = lib.heal_conv2d_tc(_p(x_split), x_split[0].numel(), N, H, W, pc.cin, Cs, in_coffset,
-                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.pad, P,
-                                _p(residual_split), res_plane, _p(residual_f32), res_cs, 0,
-                                _p(out_split), out_split[0].numel() if out_split is not None else 0,
-                                out_split.shape[-1] if out_split is not None else 0, out_coffset,
-                                _p(out_f32), out_f32.shape[-1] if out_f32 is not None else 0, out32_coffset,
+        rc = lib.heal_conv2d_tc(_p(x.t), x.plane_stride, N, H, W, pc.cin, x.cstride, in_coffset,
+                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.pad, pc.planes,
+                                _p(res_split), res_plane, _p(res_f32), res_cs, 0,
+                                _p(out.t) if out is not None else _vp(0), out.plane_stride if out is not None else 0,
+                                out.cstride if out is not None else 0, out_coffset,
+                                _p(out_f32.t) if out_f32 is not None else _vp(0),
+                                out_f32.cstride if out_f32 is not None else 0, out32_coffset,
                                 Ho, Wo, pc.cout, up, 1 if pc.relu else 0, _stream())
     check(rc, "heal_conv2d_tc")
-    return out_split, out_f32
+    return out, out_f32
+
+
+# ------------------------------------------------------------------------------------------------
+# fusion
+# ------------------------------------------------------------------------------------------------
+def pyramid_fuse_level(feat: Act, occ: torch.Tensor, theta: torch.Tensor, align_corners: bool,
+                       crop_windows: Optional[torch.Tensor] = None, out: Optional[Act] = None,
+                       out_fmt: Optional[str] = None, out_coffset: int = 0) -> Act:
+    """feat: Act (n,H,W,C); occ (n,H,W) f32 logits; theta (n,2,3) f64 -> out Act (1,H,W,C) (one scene)."""
+    _need_cuda(occ, theta)
+    n, H, W, C = feat.N, feat.H, feat.W, feat.C
+    assert occ.is_contiguous() and occ.dtype == torch.float32 and occ.numel() == n * H * W
+    th = theta.to(torch.float64).contiguous()
+    assert th.shape == (n, 2, 3)
+    if out is None:
+        out = act_empty(1, H, W, C, out_fmt or feat.fmt, feat.device)
+    cw = crop_windows.to(torch.int32).contiguous() if crop_windows is not None else None
+    fv, ov = feat.view(), out.view(out_coffset)
+    with _Prof("pyramid_fuse_level"):
+        rc = lib.heal_pyramid_fuse_level(ctypes.byref(fv), _p(occ), _p(th), _p(cw), n, H, W, C,
+                                         1 if align_corners else 0, ctypes.byref(ov), _stream())
+    check(rc, "heal_pyramid_fuse_level")
+    return out
+
+
+def att_fuse(feat: Act, theta: torch.Tensor, out: Optional[Act] = None, out_fmt: Optional[str] = None) -> Act:
+    """feat: Act (n,H,W,C), theta (n,2,3) f64 -> Act (1,H,W,C)."""
+    _need_cuda(theta)
+    n, H, W, C = feat.N, feat.H, feat.W, feat.C
+    th = theta.to(torch.float64).contiguous()
+    if out is None:
+        out = act_empty(1, H, W, C, out_fmt or feat.fmt, feat.device)
+    fv, ov = feat.view(), out.view()
+    with _Prof("att_fuse"):
+        rc = lib.heal_att_fuse(ctypes.byref(fv), _p(th), n, H, W, C, ctypes.byref(ov), _stream())
+    check(rc, "heal_att_fuse")
+    return out

@@ -24,7 +24,21 @@
 extern "C" {
 #endif
 
-#define HEAL_B200_ABI_VERSION 1
+#define HEAL_B200_ABI_VERSION 2
+
+/* Activation tensor view (channels-last).  fmt: 0 = fp32, 1 = bf16 (one plane), 2 = split-bf16
+ * (hi = bf16(x) at data, lo = bf16(x-hi) at data + plane_stride elements; x ~ hi+lo, 16 mantissa bits).
+ * cstride = elements between consecutive pixels, coffset = first channel used. */
+#define HEAL_FMT_F32 0
+#define HEAL_FMT_BF16 1
+#define HEAL_FMT_SPLIT 2
+typedef struct {
+    void* data;
+    int fmt;
+    int cstride;
+    int coffset;
+    size_t plane_stride;
+} heal_act_t;
 int heal_abi_version(void);
 /* sm_100a build check: returns 0 when a Blackwell (cc 10.x) device is current, negative otherwise. */
 int heal_device_check(void);
@@ -70,17 +84,17 @@ int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_po
 /* ---- 2-D convolution, fp32 CUDA-core path ---------------------------------------------------
  * replaces nn.Conv2d / nn.ConvTranspose2d(k==stride) + eval BatchNorm2d + ReLU (+ residual add) of
  * resblock.py:48-64,102-122, base_bev_backbone.py:40-86, base_bev_backbone_resnet.py:54-85,
- * downsample_conv.py:16-27, heter_pyramid_collab.py:102-107.
- *   weight: groups==1 : [kh][kw][Cin][w_cstride] (w_cstride >= Cout, multiple of 4), BN scale folded
- *           groups>1  : [kh*kw][Cin/groups][Cout/groups][groups] (3x3 only, Cin==Cout)
+ * downsample_conv.py:16-27, heter_pyramid_collab.py:102-107.  fp32 FMA math whatever the storage
+ * format of in / residual / out (heal_act_t).
+ *   weight: groups==1 : fp32 [kh][kw][Cin][w_cstride] (w_cstride >= Cout, multiple of 4), BN scale folded
+ *           groups>1  : fp32 [kh*kw][Cin/groups][Cout/groups][groups] (3x3 only, Cin==Cout)
  *   output pixel (oh,ow) of the (Ho,Wo) conv grid is stored at (oh*upsample+up_i, ow*upsample+up_j)
  *   of an (Ho*upsample, Wo*upsample) map: a k==stride transposed conv is upsample^2 1x1 launches. */
-int heal_conv2d_nhwc_f32(const float* in, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
-                         const float* weight, int w_cstride, const float* bias,
-                         int kh, int kw, int stride, int pad, int groups,
-                         const float* residual, int res_cstride, int res_coffset,
-                         float* out, int Ho, int Wo, int Cout, int out_cstride, int out_coffset,
-                         int upsample, int up_i, int up_j, int relu, void* stream);
+int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
+                     const float* weight, int w_cstride, const float* bias,
+                     int kh, int kw, int stride, int pad, int groups,
+                     const heal_act_t* residual, const heal_act_t* out, int Ho, int Wo, int Cout,
+                     int upsample, int up_i, int up_j, int relu, void* stream);
 
 /* ---- 2-D convolution, tcgen05 tensor-core path (stride 1) ---------------------------------------
  * Same reference ops as heal_conv2d_nhwc_f32, evaluated as an implicit GEMM with tcgen05.mma (TMEM
@@ -107,13 +121,16 @@ int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, i
  *   feat (n,H,W,C) channels-last; occ (n,H,W) logits; theta (n,2,3) f64 = affine_matrix[b,0,:n]
  *   crop_windows (n,4) i32 [h0,h1,w0,w1] (score kept inside, zeroed outside) or NULL
  *   out (H,W,C) */
-int heal_pyramid_fuse_level(const float* feat, int feat_cstride, const float* occ, const double* theta,
+int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ, const double* theta,
                             const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
-                            float* out, int out_cstride, int out_coffset, void* stream);
+                            const heal_act_t* out, void* stream);
 
 /* AttFusion.forward for one scene (opencood/models/fuse_modules/fusion_in_one.py:126-151) */
-int heal_att_fuse(const float* feat, int feat_cstride, const double* theta, int n_agents, int H, int W, int C,
-                  float* out, int out_cstride, int out_coffset, void* stream);
+int heal_att_fuse(const heal_act_t* feat, const double* theta, int n_agents, int H, int W, int C,
+                  const heal_act_t* out, void* stream);
+
+/* ---- format conversion between fp32 and (split-)bf16 channels-last buffers ------------------- */
+int heal_act_convert(const heal_act_t* src, const heal_act_t* dst, size_t num_pixels, int channels, void* stream);
 
 #ifdef __cplusplus
 }

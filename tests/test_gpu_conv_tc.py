@@ -58,13 +58,17 @@ def test_conv_tc(case, planes):
     name, N, Cin, H, W, Cout, k, pad, bias, bn, relu, res = case
     conv, bnm, x, r, y = _mk(case)
     pc = ops.pack_conv_tc(conv, bnm, relu, planes=planes).to("cuda")
-    xs = ops.split_bf16(ops.to_nhwc(x.cuda()), planes)
-    rs = ops.split_bf16(ops.to_nhwc(r.cuda()), planes) if res == "split" else None
-    rf = ops.to_nhwc(r.cuda()) if res == "f32" else None
-    o_split, o_f32 = ops.conv2d_tc(xs, pc, residual_split=rs, residual_f32=rf, want_split=True, want_f32=True)
+    fmt = "split" if planes == 2 else "bf16"
+    xs = ops.convert(ops.to_act(x.cuda()), fmt)
+    rr = None
+    if res == "split":
+        rr = ops.convert(ops.to_act(r.cuda()), fmt)
+    elif res == "f32":
+        rr = ops.to_act(r.cuda())
+    o_split, o_f32 = ops.conv2d_tc(xs, pc, residual=rr, want_split=True, want_f32=True)
     torch.cuda.synchronize()
-    got32 = o_f32.permute(0, 3, 1, 2).cpu()
-    gots = ops.merge_bf16(o_split).permute(0, 3, 1, 2).cpu()
+    got32 = ops.act_to_nchw(o_f32).cpu()
+    gots = ops.act_to_nchw(o_split).cpu()
     scale = y.abs().max().item()
     e32 = (got32 - y).abs().max().item()
     es = (gots - y).abs().max().item()
@@ -88,9 +92,9 @@ def test_deconv_tc(up):
     with torch.no_grad():
         y = F.relu(bnm(de(x)))
     pc = ops.pack_conv_tc(de, bnm, True, planes=2).to("cuda")
-    xs = ops.split_bf16(ops.to_nhwc(x.cuda()), 2)
+    xs = ops.convert(ops.to_act(x.cuda()), "split")
     buf = torch.zeros((2, 2, 16 * up, 32 * up, 384), dtype=torch.bfloat16, device="cuda")
-    ops.conv2d_tc(xs, pc, out_split=buf, out_coffset=128, want_split=True)
+    ops.conv2d_tc(xs, pc, out=ops.Act(buf, "split"), out_coffset=128)
     got = ops.merge_bf16(buf)[..., 128:256].permute(0, 3, 1, 2).cpu()
     err = (got - y).abs().max().item()
     print(f"deconv up={up}: err={err:.3e}")

@@ -131,8 +131,12 @@ def test_conv2d_f32_vs_torch(case):
         if relu:
             y = F.relu(y)
     pc = ops.pack_conv(conv, bnm, relu).to("cuda")
-    out = ops.conv2d(ops.to_nhwc(x.cuda()), pc, residual=ops.to_nhwc(r.cuda()) if res else None)
-    torch.testing.assert_close(ops.from_nhwc(out).cpu().contiguous(), y, rtol=1e-4, atol=1e-4)
+    out = ops.conv2d_simt(ops.to_act(x.cuda()), pc, residual=ops.to_act(r.cuda()) if res else None)
+    torch.testing.assert_close(ops.act_to_nchw(out).cpu().contiguous(), y, rtol=1e-4, atol=1e-4)
+    # same kernel with split-bf16 storage on both sides (fp32 math, 16-bit-mantissa storage)
+    outs = ops.conv2d_simt(ops.convert(ops.to_act(x.cuda()), "split"), pc,
+                           residual=ops.convert(ops.to_act(r.cuda()), "split") if res else None, out_fmt="split")
+    torch.testing.assert_close(ops.act_to_nchw(outs).cpu().contiguous(), y, rtol=2e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("up", [1, 2, 4])
@@ -150,7 +154,7 @@ def test_deconv_concat_slice(up):
         y = F.relu(bnm(de(x)))
     pc = ops.pack_deconv(de, bnm, True).to("cuda")
     buf = torch.full((2, 12 * up, 20 * up, 384), -7.0, device="cuda")
-    ops.conv2d(ops.to_nhwc(x.cuda()), pc, out=buf, out_coffset=128)
+    ops.conv2d_simt(ops.to_act(x.cuda()), pc, out=ops.Act(buf, "f32"), out_coffset=128)
     torch.testing.assert_close(buf[..., 128:256].permute(0, 3, 1, 2).cpu().contiguous(), y, rtol=1e-4, atol=1e-4)
     assert torch.all(buf[..., :128] == -7.0) and torch.all(buf[..., 256:] == -7.0)
 
@@ -173,8 +177,12 @@ def test_pyramid_fuse_level_vs_oracle(n, C, H, W, align):
     aff = _poses_affine(n, 0.4 * H, 0.4 * W, seed=C)
     score = torch.sigmoid(occ) + 1e-4
     ref = nets.weighted_fuse(x, score, torch.tensor([n]), aff, align)[0]
-    out = ops.pyramid_fuse_level(ops.to_nhwc(x.cuda()), occ.view(n, H, W).cuda().contiguous(), aff[0, 0, :n].cuda(), align)
-    torch.testing.assert_close(out.permute(2, 0, 1).cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
+    out = ops.pyramid_fuse_level(ops.to_act(x.cuda()), occ.view(n, H, W).cuda().contiguous(), aff[0, 0, :n].cuda(), align)
+    torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
+    outs = ops.pyramid_fuse_level(ops.convert(ops.to_act(x.cuda()), "split"), occ.view(n, H, W).cuda().contiguous(),
+                                  aff[0, 0, :n].cuda(), align)
+    assert outs.fmt == "split"
+    torch.testing.assert_close(ops.act_to_nchw(outs)[0].cpu().contiguous(), ref, rtol=2e-4, atol=2e-4)
 
 
 def test_pyramid_fuse_crop_mask_and_all_masked():
@@ -190,9 +198,9 @@ def test_pyramid_fuse_crop_mask_and_all_masked():
     for j in range(n):
         mask[j, :, win[j, 0]:win[j, 1], win[j, 2]:win[j, 3]] = 1
     ref = nets.weighted_fuse(x, score * mask, torch.tensor([n]), aff, False)[0]
-    out = ops.pyramid_fuse_level(ops.to_nhwc(x.cuda()), occ.view(n, H, W).cuda().contiguous(), aff[0, 0, :n].cuda(), False,
+    out = ops.pyramid_fuse_level(ops.to_act(x.cuda()), occ.view(n, H, W).cuda().contiguous(), aff[0, 0, :n].cuda(), False,
                                  crop_windows=win.cuda())
-    torch.testing.assert_close(out.permute(2, 0, 1).cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("n,C,H,W", [(5, 256, 32, 48), (3, 128, 24, 40), (1, 384, 8, 8)])
@@ -202,8 +210,8 @@ def test_att_fuse_vs_oracle(n, C, H, W):
     x = torch.randn(n, C, H, W, generator=gen)
     aff = _poses_affine(n, 0.4 * H, 0.4 * W, seed=n)
     ref = nets.att_fusion(x, torch.tensor([n]), aff)[0]
-    out = ops.att_fuse(ops.to_nhwc(x.cuda()), aff[0, 0, :n].cuda())
-    torch.testing.assert_close(out.permute(2, 0, 1).cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
+    out = ops.att_fuse(ops.to_act(x.cuda()), aff[0, 0, :n].cuda())
+    torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
 
 
 def test_warp_att_golden(golden_dir):
@@ -211,5 +219,5 @@ def test_warp_att_golden(golden_dir):
     import os
     from heal_b200 import ops
     g = torch.load(os.path.join(golden_dir, "warp_att.pt"), weights_only=False)
-    out = ops.att_fuse(ops.to_nhwc(g["x"].cuda()), g["affine"][0, 0, :3].cuda())
-    torch.testing.assert_close(out.permute(2, 0, 1).cpu().contiguous(), g["att"][0], rtol=1e-4, atol=1e-4)
+    out = ops.att_fuse(ops.to_act(g["x"].cuda()), g["affine"][0, 0, :3].cuda())
+    torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), g["att"][0], rtol=1e-4, atol=1e-4)
