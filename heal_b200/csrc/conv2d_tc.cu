@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                 // bf16 elements = 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB per plane
@@ -34,6 +34,8 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB per plane
 struct TcP {
     int N, Ho, Wo, Cout;          // output grid (conv resolution) and real output channels
     int taps_w, taps, pad;        // kw, kh*kw, padding
+    int stride;                   // conv stride (TMA element stride on W and H)
+    int blockdiag;                // grouped conv as block-diagonal 64x64 channel blocks: n-tile nt reads channel block nt only
     int kc_blocks;                // Cin / 64
     int TH, TW, tiles_h, tiles_w; // pixel tile and tile grid per image
     int m_tiles, n_tiles;
@@ -153,7 +155,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -166,7 +168,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.m_tiles * p.n_tiles;
-    const int kblocks = p.taps * p.kc_blocks;
+    const int kcn = p.blockdiag ? 1 : p.kc_blocks;      // channel blocks per tap visited by one tile
+    const int kblocks = p.taps * kcn;
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -178,14 +181,14 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int th_i = t2 % p.tiles_h; const int img = t2 / p.tiles_h;
                 const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / p.kc_blocks, kc = kb % p.kc_blocks;
+                    const int tap = kb / kcn, kc = p.blockdiag ? nt : kb % kcn;
                     const int r = tap / p.taps_w, s = tap % p.taps_w;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
-                    tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 + s - p.pad, h0 + r - p.pad, img, 0);
-                    tma_load_3d(sb, &tmB, bar_full + 8 * stage, kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
+                    tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, img, 0);
+                    tma_load_3d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -230,6 +233,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
         // ============================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;              // which half of the tile's column chunks this warp drains
         const int row = quarter * 32 + lane;            // accumulator row = pixel within the tile
         constexpr int CHUNK = (BLOCK_N >= 32) ? 32 : 16;
         int acc = 0; uint32_t acc_phase = 0;
@@ -246,7 +250,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < BLOCK_N / CHUNK; ++cc) {
+            for (int cc = chalf; cc < BLOCK_N / CHUNK; cc += 2) {
                 uint32_t raw[CHUNK];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * CHUNK);
                 if (CHUNK == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
@@ -368,7 +372,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& p, cuda
 
 extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
                               const void* w_packed, int w_rows, int coutp, const float* bias,
-                              int kh, int kw, int pad, int planes,
+                              int kh, int kw, int stride, int pad, int blockdiag, int planes,
                               const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                               void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
                               float* out_f32, int out32_cstride, int out32_coffset,
@@ -376,10 +380,12 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     if (!in_split || !w_packed || (!out_split && !out_f32)) return HEAL_ERR_ARG;
     if (planes != 1 && planes != 2) return HEAL_ERR_ARG;
     if ((Cin % BLOCK_K) || (in_cstride & 7) || (in_coffset & 7) || upsample < 1) return HEAL_ERR_UNSUPPORTED;
-    if (Ho != H + 2 * pad - kh + 1 || Wo != W + 2 * pad - kw + 1) return HEAL_ERR_UNSUPPORTED;   // stride 1 only
+    if (stride < 1 || stride > 2) return HEAL_ERR_UNSUPPORTED;
+    if (Ho != (H + 2 * pad - kh) / stride + 1 || Wo != (W + 2 * pad - kw) / stride + 1) return HEAL_ERR_ARG;
+    if (blockdiag && (upsample > 1 || coutp != Cin || (coutp % 64))) return HEAL_ERR_UNSUPPORTED;
     if (upsample > 1 && (kh != 1 || kw != 1)) return HEAL_ERR_UNSUPPORTED;
     const int taps = kh * kw;
-    const int block_n = coutp >= 128 ? 128 : coutp;
+    const int block_n = blockdiag ? 64 : (coutp >= 128 ? 128 : coutp);
     if (!(block_n == 16 || block_n == 32 || block_n == 64 || block_n == 128) || (coutp % block_n)) return HEAL_ERR_UNSUPPORTED;
     if (w_rows != (upsample > 1 ? upsample * upsample : taps) * coutp) return HEAL_ERR_ARG;
     PFN_tmEncodeTiled enc = get_encode();
@@ -392,7 +398,8 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     p.TW = tw; p.TH = BLOCK_M / tw;
     p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
     p.m_tiles = N * p.tiles_h * p.tiles_w;
-    p.n_tiles = w_rows / taps / block_n * (upsample > 1 ? 1 : 1);
+    p.n_tiles = w_rows / taps / block_n;
+    p.stride = stride; p.blockdiag = blockdiag;
     if (upsample > 1) p.n_tiles = w_rows / block_n;
     p.planes = planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
     p.res_split = (const __nv_bfloat16*)res_split; p.res_plane = res_plane_stride; p.res_f32 = res_f32;
@@ -405,8 +412,8 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)planes};
         cuuint64_t strides[4] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)W * in_cstride * 2, (cuuint64_t)H * W * in_cstride * 2,
                                  (cuuint64_t)in_plane_stride * 2};
-        cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1u, (cuuint32_t)planes};
-        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), 1u, (cuuint32_t)planes};
+        cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
         void* base = (void*)((const __nv_bfloat16*)in_split + in_coffset);
         if (planes == 1) { strides[3] = strides[2] * N; }
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -414,8 +421,9 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)w_rows, (cuuint64_t)planes};
-        cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)w_rows * Cin * 2};
+        const cuuint64_t wk = blockdiag ? 64 : Cin;      // K extent of the packed weight matrix
+        cuuint64_t dims[3] = {wk, (cuuint64_t)w_rows, (cuuint64_t)planes};
+        cuuint64_t strides[2] = {wk * 2, (cuuint64_t)w_rows * wk * 2};
         cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, (cuuint32_t)planes};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -341,11 +341,11 @@ def _coutp(cout: int) -> int:
 class PackedConvTC:
     """Folded + packed split-bf16 parameters for heal_conv2d_tc (tcgen05 path)."""
 
-    def __init__(self, w, bias, kh, kw, pad, cin, cout, coutp, relu, up, planes):
+    def __init__(self, w, bias, kh, kw, pad, cin, cout, coutp, relu, up, planes, stride=1, blockdiag=False, groups=1):
         self.w, self.bias = w, bias
         self.kh, self.kw, self.pad, self.cin, self.cout, self.coutp = kh, kw, pad, cin, cout, coutp
         self.relu, self.up, self.planes = relu, up, planes
-        self.stride, self.groups = 1, 1
+        self.stride, self.groups, self.blockdiag = stride, groups, blockdiag
 
     def to(self, device):
         self.w = self.w.to(device)
@@ -353,10 +353,21 @@ class PackedConvTC:
         return self
 
 
+TC_STRIDED = True      # stride-2 convs through TMA element strides
+TC_GROUPED = True      # grouped 3x3 convs as block-diagonal 64-channel blocks on the tensor cores
+
+
 def tc_eligible(conv) -> bool:
     if isinstance(conv, torch.nn.ConvTranspose2d):
         return conv.in_channels % 64 == 0 and conv.groups == 1
-    return conv.groups == 1 and conv.stride == (1, 1) and conv.in_channels % 64 == 0 and conv.dilation == (1, 1)
+    if conv.in_channels % 64 or conv.dilation != (1, 1) or conv.stride[0] != conv.stride[1]:
+        return False
+    if conv.stride[0] not in ((1, 2) if TC_STRIDED else (1,)):
+        return False
+    if conv.groups == 1:
+        return True
+    cg = conv.in_channels // conv.groups
+    return TC_GROUPED and conv.in_channels == conv.out_channels and conv.kernel_size == (3, 3) and 64 % cg == 0
 
 
 def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> PackedConvTC:
@@ -372,17 +383,30 @@ def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> P
         rows[:, :cout, :] = w.permute(2, 3, 1, 0).reshape(k * k, cout, cin)
         wp = split_bf16(rows.reshape(k * k * coutp, cin).float(), planes)
         return PackedConvTC(wp, b.float().contiguous(), 1, 1, 0, cin, cout, coutp, relu, k, planes)
-    w = conv.weight.detach().double().cpu()                # (Cout, Cin, kh, kw)
+    w = conv.weight.detach().double().cpu()                # (Cout, Cin/g, kh, kw)
     cout, cin, kh, kw = w.shape
-    assert conv.groups == 1 and conv.stride == (1, 1)
     scale, shift = _bn_scale_shift(bn, cout)
     b = shift + (conv.bias.detach().double().cpu() * scale if conv.bias is not None else 0)
     w = w * scale[:, None, None, None]
+    if conv.groups > 1:
+        # block-diagonal: row = tap*width + co, column = input channel inside co's 64-channel block
+        g, width, cg = conv.groups, cout, cin
+        assert width % 64 == 0 and 64 % cg == 0 and conv.in_channels == width
+        rows = torch.zeros((kh * kw, width, 64), dtype=torch.float64)
+        co = torch.arange(width)
+        col0 = (co // cg) * cg - (co // 64) * 64                     # first input channel of co's group, block-local
+        wt = w.permute(2, 3, 0, 1).reshape(kh * kw, width, cg)        # (tap, co, ci)
+        for ci in range(cg):
+            rows[:, co, col0 + ci] = wt[:, :, ci]
+        wp = split_bf16(rows.reshape(kh * kw * width, 64).float(), planes)
+        return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, width, width, width, relu, 1,
+                            planes, stride=conv.stride[0], blockdiag=True, groups=g)
     coutp = _coutp(cout)
     rows = torch.zeros((kh * kw, coutp, cin), dtype=torch.float64)
     rows[:, :cout, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     wp = split_bf16(rows.reshape(kh * kw * coutp, cin).float(), planes)
-    return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, cin, cout, coutp, relu, 1, planes)
+    return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, cin, cout, coutp, relu, 1, planes,
+                        stride=conv.stride[0])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -428,7 +452,7 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
     assert x.planes == pc.planes and x.planes in (1, 2)
     N, H, W = x.N, x.H, x.W
     up = pc.up
-    Ho, Wo = H + 2 * pc.pad - pc.kh + 1, W + 2 * pc.pad - pc.kw + 1
+    Ho, Wo = (H + 2 * pc.pad - pc.kh) // pc.stride + 1, (W + 2 * pc.pad - pc.kw) // pc.stride + 1
     if want_split and out is None:
         out = act_empty(N, Ho * up, Wo * up, pc.cout, x.fmt, x.device)
     if want_f32 and out_f32 is None:
@@ -441,11 +465,12 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
         else:
             assert residual.planes == pc.planes
             res_split, res_cs, res_plane = residual.t, residual.cstride, residual.plane_stride
-    fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "")
-    flops = 2.0 * N * Ho * Wo * pc.cout * pc.cin * pc.kh * pc.kw * up * up
+    fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "") + ("_grouped" if pc.blockdiag else "") + (f"_s{pc.stride}" if pc.stride > 1 else "")
+    flops = 2.0 * N * Ho * Wo * pc.cout * (pc.cin // pc.groups) * pc.kh * pc.kw * up * up
     with _Prof(fam, flops):
         rc = lib.heal_conv2d_tc(_p(x.t), x.plane_stride, N, H, W, pc.cin, x.cstride, in_coffset,
-                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.pad, pc.planes,
+                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.stride, pc.pad,
+                                1 if pc.blockdiag else 0, pc.planes,
                                 _p(res_split), res_plane, _p(res_f32), res_cs, 0,
                                 _p(out.t) if out is not None else _vp(0), out.plane_stride if out is not None else 0,
                                 out.cstride if out is not None else 0, out_coffset,

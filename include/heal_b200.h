@@ -96,7 +96,7 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
                      const heal_act_t* residual, const heal_act_t* out, int Ho, int Wo, int Cout,
                      int upsample, int up_i, int up_j, int relu, void* stream);
 
-/* ---- 2-D convolution, tcgen05 tensor-core path (stride 1) ---------------------------------------
+/* ---- 2-D convolution, tcgen05 tensor-core path ---------------------------------------------------
  * Same reference ops as heal_conv2d_nhwc_f32, evaluated as an implicit GEMM with tcgen05.mma (TMEM
  * accumulators) fed by TMA.  Activations are "split-bf16": `planes` bf16 channels-last planes
  * (planes=2: hi = bf16(x), lo = bf16(x-hi), fp32-equivalent via 3 MMAs per K step; planes=1: plain bf16).
@@ -105,10 +105,14 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
  *              transposed conv (kh=kw=1, upsample=k): w_rows = k*k*coutp, row = (i*k+j)*coutp + co;
  *              coutp = Cout padded to 16/32/64 or a multiple of 128; BN scale folded; bias fp32 [Cout]
  *   residual   split planes (res_split) or fp32 (res_f32) or neither, at output resolution
- *   outputs    split planes and/or fp32, channels-last, output map (Ho*upsample, Wo*upsample) */
+ *   outputs    split planes and/or fp32, channels-last, output map (Ho*upsample, Wo*upsample)
+ *   stride     1 or 2 (TMA element strides on W/H)
+ *   blockdiag  1: grouped 3x3 conv (Cin == Cout == coutp, channels-per-group | 64) evaluated as block-diagonal
+ *              64x64 channel blocks; w_packed is then [planes][kh*kw*coutp][64] (row = tap*coutp + co,
+ *              column = input channel within co's 64-channel block, zeros outside co's group) */
 int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
                    const void* w_packed, int w_rows, int coutp, const float* bias,
-                   int kh, int kw, int pad, int planes,
+                   int kh, int kw, int stride, int pad, int blockdiag, int planes,
                    const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                    void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
                    float* out_f32, int out32_cstride, int out32_coffset,

@@ -100,3 +100,43 @@ def test_deconv_tc(up):
     print(f"deconv up={up}: err={err:.3e}")
     assert err < 1e-3
     assert torch.all(buf[..., :128] == 0) and torch.all(buf[..., 256:] == 0)
+
+
+STRIDE_GROUP_CASES = [
+    # name, N, C, H, W, Cout, k, stride, pad, groups
+    ("s2_3x3_64", 2, 64, 32, 64, 64, 3, 2, 1, 1),
+    ("s2_3x3_canvas", 1, 64, 64, 256, 64, 3, 2, 1, 1),
+    ("s2_1x1_128_256", 1, 128, 32, 32, 256, 1, 2, 0, 1),
+    ("s2_3x3_odd", 1, 64, 31, 45, 64, 3, 2, 1, 1),
+    ("g32_cg4_s1", 2, 128, 24, 40, 128, 3, 1, 1, 32),
+    ("g32_cg8_s2", 1, 256, 32, 64, 256, 3, 2, 1, 32),
+    ("g32_cg16_s1", 1, 512, 16, 16, 512, 3, 1, 1, 32),
+    ("g32_cg16_s2", 1, 512, 17, 23, 512, 3, 2, 1, 32),
+]
+
+
+@pytest.mark.parametrize("case", STRIDE_GROUP_CASES, ids=[c[0] for c in STRIDE_GROUP_CASES])
+def test_conv_tc_stride_grouped(case):
+    from heal_b200 import ops
+    name, N, C, H, W, Cout, k, stride, pad, groups = case
+    gen = torch.Generator().manual_seed(abs(hash(name)) % 10000)
+    conv = torch.nn.Conv2d(C, Cout, k, stride=stride, padding=pad, groups=groups, bias=False)
+    bnm = torch.nn.BatchNorm2d(Cout, eps=1e-5).eval()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * (1.0 / (C // groups * k * k)) ** 0.5)
+        bnm.weight.copy_(torch.rand(Cout, generator=gen) + 0.5)
+        bnm.bias.copy_(torch.randn(Cout, generator=gen) * 0.1)
+        bnm.running_mean.copy_(torch.randn(Cout, generator=gen) * 0.1)
+        bnm.running_var.copy_(torch.rand(Cout, generator=gen) + 0.5)
+    x = torch.randn(N, C, H, W, generator=gen)
+    with torch.no_grad():
+        y = F.relu(bnm(conv(x)))
+    assert ops.tc_eligible(conv)
+    pc = ops.pack_conv_tc(conv, bnm, True, planes=2).to("cuda")
+    o, _ = ops.conv2d_tc(ops.convert(ops.to_act(x.cuda()), "split"), pc)
+    torch.cuda.synchronize()
+    got = ops.act_to_nchw(o).cpu()
+    assert got.shape == y.shape
+    err = (got - y).abs().max().item()
+    print(f"{name}: max|y|={y.abs().max().item():.3f} err={err:.3e}")
+    assert err < 1e-3
