@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(PV_WARPS * 32)
 k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ num_points,
                      const int4* __restrict__ coords, const int* __restrict__ num_voxels_dev, int M,
                      const float* __restrict__ Wf, const float* __restrict__ bf, PvCfg c,
-                     float* __restrict__ pillar_out, float* __restrict__ canvas) {
+                     float* __restrict__ pillar_out, ActV canvas) {
     __shared__ float sW[PV_CIN * PV_COUT];
     __shared__ float sB[PV_COUT];
     __shared__ __align__(16) float sF[PV_WARPS][32][12];
@@ -73,9 +73,19 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     }
     float2 o = make_float2(m0, m1);
     if (pillar_out) reinterpret_cast<float2*>(pillar_out + (size_t)v * PV_COUT)[lane] = o;
-    if (canvas) {
+    if (canvas.p) {
         size_t cell = ((size_t)cd.x * c.ny + (size_t)cd.z) * c.nx + (size_t)(cd.y + cd.w);  // z + y*nx + x, z == 0
-        reinterpret_cast<float2*>(canvas + cell * PV_COUT)[lane] = o;
+        if (canvas.fmt == 0) {
+            reinterpret_cast<float2*>(reinterpret_cast<float*>(canvas.p) + cell * canvas.cs + canvas.co)[lane] = o;
+        } else {
+            __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(canvas.p) + cell * canvas.cs + canvas.co;
+            __nv_bfloat162 h = __floats2bfloat162_rn(o.x, o.y);
+            reinterpret_cast<__nv_bfloat162*>(b)[lane] = h;
+            if (canvas.fmt == 2) {
+                float2 hf = __bfloat1622float2(h);
+                reinterpret_cast<__nv_bfloat162*>(b + canvas.plane)[lane] = __floats2bfloat162_rn(o.x - hf.x, o.y - hf.y);
+            }
+        }
     }
 }
 
@@ -85,7 +95,7 @@ extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* v
                                        const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
                                        const float* w_folded, const float* b_folded, int c_in, int c_out,
                                        const float* voxel_size3, const float* offset3, int nx, int ny,
-                                       float* pillar_features_out, float* canvas_nhwc_out, void* stream_) {
+                                       float* pillar_features_out, const heal_act_t* canvas_out, void* stream_) {
     if (!voxel_features || !voxel_num_points || !voxel_coords || !w_folded || !b_folded) return HEAL_ERR_ARG;
     if (c_in != PV_CIN || c_out != PV_COUT || max_points_per_voxel < 1 || max_points_per_voxel > 32) return HEAL_ERR_UNSUPPORTED;
     if (num_voxels <= 0) return HEAL_OK;
@@ -93,9 +103,16 @@ extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* v
     c.vx = voxel_size3[0]; c.vy = voxel_size3[1]; c.vz = voxel_size3[2];
     c.xoff = offset3[0]; c.yoff = offset3[1]; c.zoff = offset3[2];
     c.T = max_points_per_voxel; c.nx = nx; c.ny = ny;
+    ActV cv;
+    cv.p = nullptr; cv.fmt = 0; cv.cs = PV_COUT; cv.co = 0; cv.plane = 0;
+    if (canvas_out && canvas_out->data) {
+        if ((canvas_out->cstride & 1) || (canvas_out->coffset & 1)) return HEAL_ERR_UNSUPPORTED;
+        cv.p = canvas_out->data; cv.fmt = canvas_out->fmt; cv.cs = canvas_out->cstride; cv.co = canvas_out->coffset;
+        cv.plane = canvas_out->plane_stride;
+    }
     int grid = (num_voxels + PV_WARPS - 1) / PV_WARPS;
     k_pillar_vfe_scatter<<<grid, PV_WARPS * 32, 0, (cudaStream_t)stream_>>>(
         (const float4*)voxel_features, voxel_num_points, (const int4*)voxel_coords, num_voxels_dev, num_voxels,
-        w_folded, b_folded, c, pillar_features_out, canvas_nhwc_out);
+        w_folded, b_folded, c, pillar_features_out, cv);
     return heal_check_launch();
 }

@@ -27,6 +27,13 @@ class PointPillar(nn.Module):
         self.voxelize_args = args.get('voxelize', {'max_points_per_voxel': 32, 'max_voxels': 70000})
 
     def forward(self, data_dict, modality_name):
+        """reference signature: returns the (n, C, ny, nx) BEV map (logical NCHW, physically channels-last fp32)."""
+        return ops.act_to_nchw(self.forward_act(data_dict, modality_name, fmt="f32"))
+
+    def forward_act(self, data_dict, modality_name, fmt=None):
+        """internal path: the canvas as an `Act` in the conv engine's activation format (no conversion pass)."""
+        from ..engine import act_fmt
+        fmt = fmt or act_fmt()
         require_eval(self)
         inp = data_dict[f'inputs_{modality_name}']
         nvox_dev = None
@@ -44,5 +51,5 @@ class PointPillar(nn.Module):
         w, b = self.pillar_vfe.folded()
         _, canvas = ops.pillar_vfe_scatter(vf, vn, vc, w, b, self.voxel_size, self.lidar_range,
                                            nx=self.scatter.nx, ny=self.scatter.ny, batch_size=batch_size,
-                                           num_voxels_dev=nvox_dev)
+                                           num_voxels_dev=nvox_dev, canvas_fmt=fmt)
         return canvas

@@ -118,9 +118,10 @@ class HeterPyramidCollab(nn.Module):
         for m in self.modality_name_list:
             if m not in count:
                 continue
-            f = getattr(self, f"encoder_{m}")(data_dict, m)                       # logical NCHW, physical NHWC
+            enc = getattr(self, f"encoder_{m}")
+            f = enc.forward_act(data_dict, m) if hasattr(enc, "forward_act") else ops.to_act(enc(data_dict, m))
             bb = getattr(self, f"backbone_{m}")
-            f = bb.decode_nhwc(bb.multiscale_nhwc(ops.to_act(f)))                 # Act
+            f = bb.decode_nhwc(bb.multiscale_nhwc(f))                             # Act
             # aligner_m is the identity for every in-scope modality (AlignNet raises otherwise)
             if self.sensor_type_dict[m] == "camera":
                 f = self._center_crop_nhwc(f, int(f.H * getattr(self, f"crop_ratio_H_{m}")),

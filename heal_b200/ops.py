@@ -243,8 +243,8 @@ def fold_linear_bn(weight: torch.Tensor, bn_w, bn_b, bn_mean, bn_var, eps: float
 def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded,
                        voxel_size, lidar_range, nx: int, ny: int, batch_size: int,
                        want_pillar_features: bool = False, want_canvas: bool = True,
-                       num_voxels_dev: Optional[torch.Tensor] = None):
-    """Returns (pillar_features (M,64) | None, canvas logical (B,64,ny,nx) channels-last fp32 | None)."""
+                       num_voxels_dev: Optional[torch.Tensor] = None, canvas_fmt: str = "f32"):
+    """Returns (pillar_features (M,64) | None, canvas Act (B,ny,nx,64) in `canvas_fmt` | None)."""
     _need_cuda(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded)
     M, T, C = voxel_features.shape
     assert C == 4
@@ -257,12 +257,20 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
     vs = [float(v) for v in voxel_size]
     off = [vs[i] / 2 + float(lidar_range[i]) for i in range(3)]
     with _Prof("pillar_vfe_scatter(+canvas memset)"):
-        canvas = torch.zeros((batch_size, ny, nx, cout), dtype=torch.float32, device=dev) if want_canvas else None
+        canvas, cview = None, None
+        if want_canvas:
+            if canvas_fmt == "f32":
+                canvas = Act(torch.zeros((batch_size, ny, nx, cout), dtype=torch.float32, device=dev), "f32")
+            else:
+                canvas = Act(torch.zeros((2 if canvas_fmt == "split" else 1, batch_size, ny, nx, cout),
+                                         dtype=torch.bfloat16, device=dev), canvas_fmt)
+            cv = canvas.view()
+            cview = ctypes.byref(cv)
         rc = lib.heal_pillar_vfe_scatter(_p(vf), _p(npts), _p(coords), _p(num_voxels_dev), M, T,
                                          _p(w_folded), _p(b_folded), w_folded.shape[0], cout,
-                                         _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), _p(canvas), _stream())
+                                         _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), cview, _stream())
     check(rc, "heal_pillar_vfe_scatter")
-    return pf, (from_nhwc(canvas) if canvas is not None else None)
+    return pf, canvas
 
 
 # ------------------------------------------------------------------------------------------------

@@ -73,13 +73,14 @@ int heal_mean_vfe(const float* voxels, const int* num_points, int num_voxels, in
  * and PointPillarScatter.forward (opencood/models/sub_modules/point_pillar_scatter.py:19-77).
  *   w_folded (10,64) = linear.weight^T * bn_scale, b_folded (64) = bn_shift (folded on the host, fp64)
  *   offset3_host = voxel_size/2 + range_min (x,y,z)
- *   pillar_features_out (M,64) or NULL; canvas_nhwc_out (B,ny,nx,64) pre-zeroed, or NULL
+ *   pillar_features_out (M,64) fp32 or NULL; canvas_out: (B,ny,nx,64) channels-last view in any storage
+ *   format, pre-zeroed by the caller, or NULL
  *   num_voxels_dev: optional device count (row 0 used) so a graph-captured frame needs no host sync */
 int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_points, const int* voxel_coords,
                             const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
                             const float* w_folded, const float* b_folded, int c_in, int c_out,
                             const float* voxel_size3_host, const float* offset3_host, int nx, int ny,
-                            float* pillar_features_out, float* canvas_nhwc_out, void* stream);
+                            float* pillar_features_out, const heal_act_t* canvas_out, void* stream);
 
 /* ---- 2-D convolution, fp32 CUDA-core path ---------------------------------------------------
  * replaces nn.Conv2d / nn.ConvTranspose2d(k==stride) + eval BatchNorm2d + ReLU (+ residual add) of

@@ -82,8 +82,12 @@ def test_pillar_vfe_scatter_vs_oracle():
     pf, canvas = ops.pillar_vfe_scatter(col["voxel_features"].cuda(), col["voxel_num_points"].cuda(), col["voxel_coords"].cuda(),
                                         w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2, want_pillar_features=True)
     torch.testing.assert_close(pf.cpu(), ref_pf, rtol=1e-4, atol=1e-4)
-    assert canvas.shape == (2, 64, 512, 512)
-    torch.testing.assert_close(canvas.cpu().contiguous(), ref_canvas, rtol=1e-4, atol=1e-4)
+    cv = ops.act_to_nchw(canvas)
+    assert cv.shape == (2, 64, 512, 512)
+    torch.testing.assert_close(cv.cpu().contiguous(), ref_canvas, rtol=1e-4, atol=1e-4)
+    _, canvas_s = ops.pillar_vfe_scatter(col["voxel_features"].cuda(), col["voxel_num_points"].cuda(), col["voxel_coords"].cuda(),
+                                         w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2, canvas_fmt="split")
+    torch.testing.assert_close(ops.act_to_nchw(canvas_s).cpu().contiguous(), ref_canvas, rtol=2e-4, atol=2e-4)
 
 
 CONV_CASES = [
