@@ -198,6 +198,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -214,6 +215,22 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per 16-element K step
+                        if (p.blockdiag) {
+                            // Grouped conv: channels-per-group divides 16, so output channels [16k,16k+16) of this 64-block
+                            // depend only on input channels [16k,16k+16): one M128 x N16 x K16 MMA per 16-channel
+                            // sub-block (B rows 16k.. = +2048 B, D columns 16k..) instead of a 64x64 block.
+                            const uint64_t bo = ko + (uint64_t)((k * 16 * 128) >> 4);
+                            const uint32_t td = tmem_d + (uint32_t)(k * 16);
+                            const uint32_t f0 = (kb == 0) ? 0u : 1u;
+                            if (p.planes == 2) {
+                                umma_bf16(td, a_lo + ko, b_hi + bo, idesc16, f0);
+                                umma_bf16(td, a_hi + ko, b_lo + bo, idesc16, 1u);
+                                umma_bf16(td, a_hi + ko, b_hi + bo, idesc16, 1u);
+                            } else {
+                                umma_bf16(td, a_hi + ko, b_hi + bo, idesc16, f0);
+                            }
+                            continue;
+                        }
                         const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
                         if (p.planes == 2) {
                             umma_bf16(tmem_d, a_lo + ko, b_hi + ko, idesc, first);

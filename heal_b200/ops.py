@@ -375,7 +375,7 @@ def tc_eligible(conv) -> bool:
     if conv.groups == 1:
         return True
     cg = conv.in_channels // conv.groups
-    return TC_GROUPED and conv.in_channels == conv.out_channels and conv.kernel_size == (3, 3) and 64 % cg == 0
+    return TC_GROUPED and conv.in_channels == conv.out_channels and conv.kernel_size == (3, 3) and 16 % cg == 0
 
 
 def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> PackedConvTC:
@@ -399,7 +399,7 @@ def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> P
     if conv.groups > 1:
         # block-diagonal: row = tap*width + co, column = input channel inside co's 64-channel block
         g, width, cg = conv.groups, cout, cin
-        assert width % 64 == 0 and 64 % cg == 0 and conv.in_channels == width
+        assert width % 64 == 0 and 16 % cg == 0 and conv.in_channels == width
         rows = torch.zeros((kh * kw, width, 64), dtype=torch.float64)
         co = torch.arange(width)
         col0 = (co // cg) * cg - (co // 64) * 64                     # first input channel of co's group, block-local
