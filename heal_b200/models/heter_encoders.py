@@ -53,3 +53,155 @@ class PointPillar(nn.Module):
                                            nx=self.scatter.nx, ny=self.scatter.ny, batch_size=batch_size,
                                            num_voxels_dev=nvox_dev, canvas_fmt=fmt)
         return canvas
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Lift-Splat-Shoot camera encoder
+# ---------------------------------------------------------------------------------------------------------
+def gen_dx_bx(xbound, ybound, zbound):
+    """opencood/utils/camera_utils.py:129-134 (fp32 tensors, same construction)."""
+    dx = torch.Tensor([row[2] for row in [xbound, ybound, zbound]])
+    bx = torch.Tensor([row[0] + row[2] / 2.0 for row in [xbound, ybound, zbound]])
+    nx = torch.LongTensor([(row[1] - row[0]) / row[2] for row in [xbound, ybound, zbound]])
+    return dx, bx, nx
+
+
+def depth_discretization(depth_min, depth_max, num_bins, mode):
+    """opencood/utils/camera_utils.py:187-196."""
+    if mode == "UD":
+        return depth_min + (depth_max - depth_min) / num_bins * np.arange(num_bins)
+    if mode == "LID":
+        bin_size = 2 * (depth_max - depth_min) / (num_bins * (1 + num_bins))
+        return depth_min + bin_size * (np.arange(num_bins) * np.arange(1, 1 + num_bins)) / 2
+    raise NotImplementedError(mode)
+
+
+class CamEncode_Resnet101(nn.Module):
+    """Image trunk + depth / image heads (opencood/models/sub_modules/lss_submodule.py:140-233), same attribute
+    names -> same state-dict keys.  The trunk (first two ResNet-101 stages) is a 'next' row and
+    runs on PyTorch/cuDNN; the depth softmax (x) feature outer product that follows it is NOT computed here - it
+    is fused into the BEV-pool kernel."""
+
+    def __init__(self, D, C, downsample, ddiscr, mode, use_gt_depth=False, depth_supervision=True):
+        super().__init__()
+        from torchvision.models.resnet import resnet101
+        self.D, self.C, self.downsample = D, C, downsample
+        self.d_min, self.d_max, self.num_bins = ddiscr[0], ddiscr[1], ddiscr[2]
+        self.mode, self.use_gt_depth, self.depth_supervision = mode, use_gt_depth, depth_supervision
+        trunk = resnet101(weights=None, zero_init_residual=True)
+        self.conv1, self.bn1, self.relu, self.maxpool = trunk.conv1, trunk.bn1, nn.ReLU(), trunk.maxpool
+        self.layer1, self.layer2, self.layer3 = trunk.layer1, trunk.layer2, nn.Identity()
+        if use_gt_depth:
+            raise NotImplementedError("use_depth_gt is a training-time option outside the inference hot path")
+        self.depth_head = nn.Conv2d(512, self.D, kernel_size=1, padding=0)
+        self.image_head = nn.Conv2d(512, self.C, kernel_size=1, padding=0)
+
+    def heads(self, x):
+        """x (BN, 3|4, H, W) -> (depth_logits (BN,D,fH,fW), feat (BN,C,fH,fW))"""
+        f = self.layer2(self.layer1(self.maxpool(self.relu(self.bn1(self.conv1(x[:, :3].clone()))))))
+        return self.depth_head(f), self.image_head(f)
+
+
+class LiftSplatShoot(nn.Module):
+    """opencood/models/heter_encoders.py:83-241 with the reference's ctor argument and forward signature."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.grid_conf = args['grid_conf']
+        self.data_aug_conf = args['data_aug_conf']
+        dx, bx, nx = gen_dx_bx(self.grid_conf['xbound'], self.grid_conf['ybound'], self.grid_conf['zbound'])
+        self.register_buffer("dx", dx.clone(), persistent=False)
+        self.register_buffer("bx", bx.clone(), persistent=False)
+        self.register_buffer("nx", nx.clone(), persistent=False)
+        self.depth_supervision = args['depth_supervision']
+        self.downsample = args['img_downsample']
+        self.camC = args['img_features']
+        self.register_buffer("frustum", self.create_frustum(), persistent=False)
+        self.D = self.frustum.shape[0]
+        self.camera_encoder_type = args['camera_encoder']
+        if self.camera_encoder_type != 'Resnet101':
+            raise NotImplementedError("camera_encoder 'EfficientNet' needs efficientnet_pytorch + pretrained download; "
+                                      "use 'Resnet101' (SURVEY.md 8c)")
+        self.camencode = CamEncode_Resnet101(self.D, self.camC, self.downsample, self.grid_conf['ddiscr'],
+                                             self.grid_conf['mode'], args['use_depth_gt'], args['depth_supervision'])
+        if int(self.nx[2]) != 1:
+            raise NotImplementedError("heal_lss_pool supports a single z slice (every HEAL yaml uses zbound with nz == 1)")
+
+    def create_frustum(self):
+        ogfH, ogfW = self.data_aug_conf['final_dim']
+        fH, fW = ogfH // self.downsample, ogfW // self.downsample
+        ds = torch.tensor(depth_discretization(*self.grid_conf['ddiscr'], self.grid_conf['mode']), dtype=torch.float) \
+            .view(-1, 1, 1).expand(-1, fH, fW)
+        D = ds.shape[0]
+        xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+        ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+        return torch.stack((xs, ys, ds), -1).contiguous()
+
+    def bev_from_heads(self, depth_logits, feat, rots, trans, intrins, post_rots, post_trans):
+        """The kernel part: geometry -> cell index -> fused softmax (x) feat -> BEV pool.  Returns Act f32 (B,ny,nx,C)."""
+        B, N = trans.shape[:2]
+        post_inv = torch.inverse(post_rots).reshape(B * N, 3, 3)          # 3x3 algebra exactly as the reference (:135,:142)
+        combine = rots.matmul(torch.inverse(intrins)).reshape(B * N, 3, 3)
+        lower = (self.bx - self.dx / 2.).tolist()
+        cell = ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
+                                  lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
+        return ops.lss_pool(depth_logits, feat, cell, N, int(self.nx[0]), int(self.nx[1]))
+
+    def forward_act(self, data_dict, modality_name, fmt=None):
+        require_eval(self)
+        d = data_dict[f'inputs_{modality_name}']
+        x = d['imgs']
+        B, N, C, imH, imW = x.shape
+        depth_logits, feat = self.camencode.heads(x.view(B * N, C, imH, imW))
+        if self.depth_supervision:
+            self.depth_items = (depth_logits, None)
+        return self.bev_from_heads(depth_logits, feat, d['rots'], d['trans'], d['intrins'], d['post_rots'], d['post_trans'])
+
+    def forward(self, data_dict, modality_name):
+        return ops.act_to_nchw(self.forward_act(data_dict, modality_name))
+
+
+class LiftSplatShootVoxel(LiftSplatShoot):
+    """heter_encoders.py:244-301: max over z instead of concat; identical for the single-slice grids HEAL uses."""
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SECOND
+# ---------------------------------------------------------------------------------------------------------
+class SECOND(nn.Module):
+    """heter_encoders.py:52-81: MeanVFE -> VoxelBackBone8x (sparse 3-D convs) -> HeightCompression."""
+
+    def __init__(self, args):
+        super().__init__()
+        from .sub_modules.mean_vfe import MeanVFE
+        from .sub_modules.sparse_backbone_3d import VoxelBackBone8x
+        from .sub_modules.height_compression import HeightCompression
+        lidar_range = np.array(args['lidar_range'])
+        grid_size = np.round((lidar_range[3:6] - lidar_range[:3]) / np.array(args['voxel_size'])).astype(np.int64)
+        self.vfe = MeanVFE(args['mean_vfe'], args['mean_vfe']['num_point_features'])
+        self.spconv_block = VoxelBackBone8x(args['spconv'], input_channels=args['spconv']['num_features_in'], grid_size=grid_size)
+        self.map_to_bev = HeightCompression(args['map2bev'])
+        self.voxel_size = [float(v) for v in args['voxel_size']]
+        self.lidar_range = [float(v) for v in args['lidar_range']]
+        self.voxelize_args = args.get('voxelize', {'max_points_per_voxel': 5, 'max_voxels': 70000})
+
+    def forward_act(self, data_dict, modality_name, fmt=None):
+        require_eval(self)
+        inp = data_dict[f'inputs_{modality_name}']
+        rows_dev = None
+        if 'voxel_features' in inp:
+            vf, vc, vn = inp['voxel_features'], inp['voxel_coords'], inp['voxel_num_points']
+            batch_size = inp.get('batch_size')
+            if batch_size is None:
+                batch_size = int(vc[:, 0].max().item()) + 1          # host sync, as the reference (heter_encoders.py:70)
+        else:
+            vf, vc, vn, nvox = ops.voxelize(inp['points'], inp['agent_offsets'], self.lidar_range, self.voxel_size,
+                                            self.voxelize_args['max_points_per_voxel'], self.voxelize_args['max_voxels'])
+            rows_dev = nvox[0:1]
+            batch_size = inp['agent_offsets'].numel() - 1
+        feats = ops.mean_vfe(vf.contiguous(), vn)
+        out, _ = self.spconv_block.forward_sparse(feats, vc, batch_size, rows_dev)
+        return self.map_to_bev.forward_act(out)
+
+    def forward(self, data_dict, modality_name):
+        return ops.act_to_nchw(self.forward_act(data_dict, modality_name))

@@ -524,3 +524,135 @@ def att_fuse(feat: Act, theta: torch.Tensor, out: Optional[Act] = None, out_fmt:
         rc = lib.heal_att_fuse(ctypes.byref(fv), _p(th), n, H, W, C, ctypes.byref(ov), _stream())
     check(rc, "heal_att_fuse")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Lift-Splat-Shoot
+# ------------------------------------------------------------------------------------------------
+def lss_cell_index(frustum, post_rots_inv, post_trans, combine, trans, lower, dx, nx) -> torch.Tensor:
+    """frustum (D,fH,fW,3); per-image 3x3 / 3-vectors (BN,...) -> int32 (BN,D,fH,fW) BEV cell or -1."""
+    _need_cuda(frustum, post_rots_inv, post_trans, combine, trans)
+    D, fH, fW, _ = frustum.shape
+    BN = post_trans.shape[0]
+    cell = torch.empty((BN, D, fH, fW), dtype=torch.int32, device=frustum.device)
+    with _Prof("lss_cell_index"):
+        rc = lib.heal_lss_cell_index(_p(frustum.contiguous().float()), D, fH, fW, _p(post_rots_inv.contiguous().float()),
+                                     _p(post_trans.contiguous().float()), _p(combine.contiguous().float()),
+                                     _p(trans.contiguous().float()), BN, _host_f32(lower), _host_f32(dx), _host_i32(nx),
+                                     _p(cell), _stream())
+    check(rc, "heal_lss_cell_index")
+    return cell
+
+
+def lss_pool(depth_logits, feat, cell, cams_per_agent: int, nx, ny) -> Act:
+    """depth_logits (BN,D,fH,fW), feat (BN,C,fH,fW) f32 NCHW, cell (BN,D,fH,fW) -> Act f32 (agents, ny, nx, C)."""
+    _need_cuda(depth_logits, feat, cell)
+    BN, D, fH, fW = depth_logits.shape
+    C = feat.shape[1]
+    agents = BN // cams_per_agent
+    with _Prof("lss_pool(+bev memset)"):
+        out = torch.zeros((agents, ny, nx, C), dtype=torch.float32, device=feat.device)
+        rc = lib.heal_lss_pool(_p(depth_logits.contiguous().float()), _p(feat.contiguous().float()), _p(cell.contiguous()),
+                               BN, cams_per_agent, D, C, fH, fW, nx * ny, _p(out), _stream())
+    check(rc, "heal_lss_pool")
+    return Act(out, "f32")
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse 3-D convolution (SECOND)
+# ------------------------------------------------------------------------------------------------
+class SparseTensor:
+    """feats (cap,C) f32 | None, coords (cap,4) i32 [b,z,y,x], rows_dev (1,) i32 device count or None (= cap rows live),
+    spatial_shape [Z,Y,X], batch.  `table` (keys, vals) maps a site to its row (built on demand)."""
+
+    def __init__(self, feats, coords, rows_dev, spatial_shape, batch, table=None):
+        self.feats, self.coords, self.rows_dev = feats, coords, rows_dev
+        self.spatial_shape, self.batch, self.table = [int(v) for v in spatial_shape], int(batch), table
+        self.capacity = coords.shape[0]
+
+    def with_feats(self, feats):
+        return SparseTensor(feats, self.coords, self.rows_dev, self.spatial_shape, self.batch, self.table)
+
+    def dense(self):
+        """(B, C, D, H, W) like spconv's SparseConvTensor.dense() (test / API helper; one host sync)."""
+        m = int(self.rows_dev[0].item()) if self.rows_dev is not None else self.capacity
+        m = min(m, self.capacity)
+        c = self.coords[:m].long()
+        out = torch.zeros((self.batch, self.feats.shape[1], *self.spatial_shape), dtype=torch.float32, device=self.feats.device)
+        out[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]] = self.feats[:m]
+        return out
+
+
+def sp_build_table(st: SparseTensor):
+    if st.table is None:
+        ts = lib.heal_spconv_table_size(st.capacity)
+        keys = torch.empty((ts,), dtype=torch.int32, device=st.coords.device)
+        vals = torch.empty((ts,), dtype=torch.int32, device=st.coords.device)
+        with _Prof("spconv_rulebook"):
+            rc = lib.heal_spconv_build_table(_p(st.coords), _p(st.rows_dev), st.capacity, _host_i32(st.spatial_shape), st.batch,
+                                             _p(keys), _p(vals), _stream())
+        check(rc, "heal_spconv_build_table")
+        st.table = (keys, vals)
+    return st.table
+
+
+def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
+    keys, vals = sp_build_table(st)
+    K = int(ksize[0] * ksize[1] * ksize[2])
+    nbr = torch.empty((st.capacity, K), dtype=torch.int32, device=st.coords.device)
+    with _Prof("spconv_rulebook"):
+        rc = lib.heal_spconv_subm_neighbors(_p(st.coords), _p(st.rows_dev), st.capacity, _host_i32(st.spatial_shape),
+                                            _host_i32(ksize), _p(keys), _p(vals), _p(nbr), _stream())
+    check(rc, "heal_spconv_subm_neighbors")
+    return nbr
+
+
+def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int] = None):
+    """SparseConv3d rulebook: returns (output SparseTensor without feats, nbr (out_cap, K))."""
+    oshape = [(st.spatial_shape[i] + 2 * pad[i] - ksize[i]) // stride[i] + 1 for i in range(3)]
+    K = int(ksize[0] * ksize[1] * ksize[2])
+    if out_capacity is None:
+        fan = 1
+        for i in range(3):
+            fan *= -(-ksize[i] // stride[i])
+        out_capacity = int(min(st.capacity * fan, st.batch * oshape[0] * oshape[1] * oshape[2]))
+    dev = st.coords.device
+    ts = lib.heal_spconv_table_size(out_capacity)
+    okeys = torch.empty((ts,), dtype=torch.int32, device=dev)
+    ovals = torch.empty((ts,), dtype=torch.int32, device=dev)
+    ocoords = torch.empty((out_capacity, 4), dtype=torch.int32, device=dev)
+    orows = torch.zeros((1,), dtype=torch.int32, device=dev)
+    nbr = torch.empty((out_capacity, K), dtype=torch.int32, device=dev)
+    wsb = lib.heal_spconv_strided_workspace(st.capacity, out_capacity, K)
+    ws = _workspace(dev, wsb)
+    with _Prof("spconv_rulebook"):
+        rc = lib.heal_spconv_strided_rulebook(_p(st.coords), _p(st.rows_dev), st.capacity, _host_i32(oshape), st.batch,
+                                              _host_i32(ksize), _host_i32(stride), _host_i32(pad), out_capacity,
+                                              _p(ocoords), _p(orows), _p(okeys), _p(ovals), _p(nbr), _p(ws), ws.numel(), _stream())
+    check(rc, "heal_spconv_strided_rulebook")
+    return SparseTensor(None, ocoords, orows, oshape, st.batch, (okeys, ovals)), nbr
+
+
+def sp_gather_gemm(feats: torch.Tensor, nbr: torch.Tensor, rows_dev, weight: torch.Tensor, bias, relu: bool) -> torch.Tensor:
+    """feats (Min,Cin) f32; nbr (cap,K) i32; weight (K,Cin,Cout) f32 (BN folded) -> (cap,Cout) f32."""
+    _need_cuda(feats, nbr, weight)
+    cap, K = nbr.shape
+    Kw, cin, cout = weight.shape
+    assert Kw == K and feats.shape[1] == cin and feats.is_contiguous()
+    out = torch.empty((cap, cout), dtype=torch.float32, device=feats.device)
+    with _Prof("spconv_gather_gemm", 2.0 * cap * K * cin * cout):
+        rc = lib.heal_spconv_gather_gemm(_p(feats), _p(nbr), _p(rows_dev), cap, K, _p(weight), _p(bias), cin, cout,
+                                         1 if relu else 0, _p(out), _stream())
+    check(rc, "heal_spconv_gather_gemm")
+    return out
+
+
+def sparse_to_bev(st: SparseTensor) -> Act:
+    """HeightCompression: (B, H, W, C*D) channels-last fp32 with channel = c*D + z."""
+    D, H, W = st.spatial_shape
+    C = st.feats.shape[1]
+    with _Prof("sparse_to_bev(+memset)"):
+        out = torch.zeros((st.batch, H, W, C * D), dtype=torch.float32, device=st.feats.device)
+        rc = lib.heal_sparse_to_bev(_p(st.feats), _p(st.coords), _p(st.rows_dev), st.capacity, C, D, H, W, _p(out), _stream())
+    check(rc, "heal_sparse_to_bev")
+    return Act(out, "f32")

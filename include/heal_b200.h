@@ -134,6 +134,54 @@ int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ, const doub
 int heal_att_fuse(const heal_act_t* feat, const double* theta, int n_agents, int H, int W, int C,
                   const heal_act_t* out, void* stream);
 
+/* ---- Lift-Splat-Shoot ------------------------------------------------------------------------
+ * heal_lss_cell_index replaces LiftSplatShoot.get_geometry + the index half of voxel_pooling
+ * (opencood/models/heter_encoders.py:125-147, :173-185): for every frustum point of every camera image
+ * the BEV cell (z*ny + y)*nx + x, or -1 when outside the grid (`.long()` truncation kept).
+ *   frustum (D,fH,fW,3) f32; post_rots_inv / combine (BN,3,3) = inverse(post_rots), rots@inverse(intrins)
+ *   (tiny 3x3 algebra done by the caller exactly as the reference does); post_trans / trans (BN,3)
+ *   lower3 = bx - dx/2, dx3, nx3: HOST arrays (x,y,z) in the reference's fp32 values
+ * heal_lss_pool replaces CamEncode's depth softmax (x) feature outer product
+ * (opencood/models/sub_modules/lss_submodule.py:132-134, :227-229) and voxel_pooling's per-cell sum
+ * (heter_encoders.py:188-212): bev_out (agents, nz*ny*nx, C) channels-last fp32, pre-zeroed (nz == 1 gives
+ * the reference's (B,C,ny,nx) map). depth_logits (BN,D,fH,fW), feat (BN,C,fH,fW) as the torch heads emit them. */
+int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,
+                        const float* post_rots_inv, const float* post_trans, const float* combine, const float* trans,
+                        int num_images, const float* lower3_host, const float* dx3_host, const int* nx3_host,
+                        int* cell_out, void* stream);
+int heal_lss_pool(const float* depth_logits, const float* feat, const int* cell, int num_images, int cams_per_agent,
+                  int D, int C, int fH, int fW, int cells_per_agent, float* bev_out, void* stream);
+
+/* ---- sparse 3-D convolution (SECOND VoxelBackBone8x) + HeightCompression ------------------------
+ * Replaces the spconv calls of opencood/models/sub_modules/sparse_backbone_3d.py:48-91,:114-130 and
+ * height_compression.py:21-23.  A sparse tensor = feats (rows,C) f32 + coords (rows,4) i32 [b,z,y,x] + a device
+ * row count; `*_capacity` bounds the rows, `*_rows_dev` (nullable) is the live count.  A hash table
+ * (keys u32, vals i32, heal_spconv_table_size(capacity) entries each) maps a site to its row.
+ * Rulebooks are output-stationary: nbr[row][k] = input row under kernel offset k (z-major, then y, x) or -1.
+ *  - build_table          site -> row map of an existing tensor (first level, from the voxelizer's coords)
+ *  - subm_neighbors       SubMConv3d rulebook (output sites = input sites), shared by every conv with the same indice_key
+ *  - strided_rulebook     SparseConv3d: output sites (deterministic order), their table, and the rulebook
+ *  - gather_gemm          out[r] = act(bias + sum_k in[nbr[r][k]] . W[k]),  W fp32 [kvol][Cin][Cout] with BN folded
+ *  - sparse_to_bev        .dense() + view(N, C*D, H, W): bev_out (B,H,W,C*D) channels-last fp32, pre-zeroed, channel = c*D+z */
+size_t heal_spconv_table_size(int capacity);
+int heal_spconv_build_table(const int* coords, const int* num_rows_dev, int capacity, const int* spatial_shape3_host, int batch,
+                            uint32_t* table_keys, int* table_vals, void* stream);
+int heal_spconv_subm_neighbors(const int* coords, const int* num_rows_dev, int capacity, const int* spatial_shape3_host,
+                               const int* ksize3_host, const uint32_t* table_keys, const int* table_vals,
+                               int* nbr_out, void* stream);
+size_t heal_spconv_strided_workspace(int in_capacity, int out_capacity, int kvol);
+int heal_spconv_strided_rulebook(const int* in_coords, const int* in_rows_dev, int in_capacity,
+                                 const int* out_spatial_shape3_host, int batch,
+                                 const int* ksize3_host, const int* stride3_host, const int* pad3_host,
+                                 int out_capacity, int* out_coords, int* out_rows_dev,
+                                 uint32_t* out_table_keys, int* out_table_vals, int* nbr_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int heal_spconv_gather_gemm(const float* in_feats, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,
+                            const float* weight, const float* bias, int c_in, int c_out, int relu,
+                            float* out_feats, void* stream);
+int heal_sparse_to_bev(const float* feats, const int* coords, const int* rows_dev, int capacity, int C, int D, int H, int W,
+                       float* bev_out, void* stream);
+
 /* ---- format conversion between fp32 and (split-)bf16 channels-last buffers ------------------- */
 int heal_act_convert(const heal_act_t* src, const heal_act_t* dst, size_t num_pixels, int channels, void* stream);
 

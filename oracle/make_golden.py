@@ -38,6 +38,13 @@ def small_model_args():
     }
 
 
+def lss_small_cfg():
+    return {"grid_conf": {"xbound": [-12.8, 12.8, 0.4], "ybound": [-12.8, 12.8, 0.4], "zbound": [-10, 10, 20.0],
+                          "ddiscr": [2, 30, 16], "mode": "LID"},
+            "data_aug_conf": {"final_dim": [64, 128]}, "img_downsample": 8, "img_features": 32,
+            "camera_encoder": "Resnet101", "use_depth_gt": False, "depth_supervision": False}
+
+
 def small_scene(seed=7, n_agents=3, pts_per_agent=1500):
     rng = np.random.default_rng(seed)
     per_agent = []
@@ -115,6 +122,36 @@ def main():
         y = bbm({"spatial_features": xin})["spatial_features_2d"]
     torch.save({"cfg": cfg, "shapes": bshapes, "x": xin, "y_s": y[:, ::4].contiguous()}, os.path.join(OUT, "base_bev_backbone_small.pt"))
     print("base_bev_backbone_small:", tuple(y.shape))
+    # ---- 4. Lift-Splat-Shoot geometry + voxel pooling (reference methods on a ctor-less instance) ------
+    from opencood.models.heter_encoders import LiftSplatShoot
+    from opencood.utils.camera_utils import gen_dx_bx
+    from heal_b200 import synth
+    lcfg = lss_small_cfg()
+    obj = LiftSplatShoot.__new__(LiftSplatShoot)
+    torch.nn.Module.__init__(obj)
+    obj.grid_conf, obj.data_aug_conf, obj.downsample = lcfg["grid_conf"], lcfg["data_aug_conf"], lcfg["img_downsample"]
+    obj.dx, obj.bx, obj.nx = gen_dx_bx(lcfg["grid_conf"]["xbound"], lcfg["grid_conf"]["ybound"], lcfg["grid_conf"]["zbound"])
+    obj.frustum = obj.create_frustum()
+    obj.use_quickcumsum = True
+    D, fH, fW, _ = obj.frustum.shape
+    Bn, Nc, Cc = 2, 2, 32
+    rots, trans, intr, post_rots, post_trans = [torch.from_numpy(a) for a in synth.camera_rig(Bn, Nc, 64, 128)]
+    gl = torch.Generator().manual_seed(21)
+    post_rots = post_rots.clone()
+    post_rots[:, :, 0, 0] = 0.9 + 0.2 * torch.rand(Bn, Nc, generator=gl)
+    post_rots[:, :, 1, 1] = post_rots[:, :, 0, 0]
+    post_trans = post_trans.clone()
+    post_trans[:, :, :2] = torch.randn(Bn, Nc, 2, generator=gl) * 3
+    depth_logits = torch.randn(Bn * Nc, D, fH, fW, generator=gl) * 2
+    feat = torch.randn(Bn * Nc, Cc, fH, fW, generator=gl)
+    with torch.no_grad():
+        geom = obj.get_geometry(rots, trans, intr, post_rots, post_trans)
+        new_x = torch.softmax(depth_logits, dim=1).unsqueeze(1) * feat.unsqueeze(2)        # lss_submodule.py:228-229
+        xx = new_x.view(Bn, Nc, Cc, D, fH, fW).permute(0, 1, 3, 4, 5, 2)                   # heter_encoders.py:156-157
+        bev = obj.voxel_pooling(geom, xx)
+    torch.save({"cfg": lcfg, "rots": rots, "trans": trans, "intrins": intr, "post_rots": post_rots, "post_trans": post_trans,
+                "depth_logits": depth_logits, "feat": feat, "geom": geom, "bev": bev}, os.path.join(OUT, "lss_small.pt"))
+    print("lss_small:", tuple(geom.shape), tuple(bev.shape), float(bev.abs().max()))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

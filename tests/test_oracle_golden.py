@@ -52,3 +52,20 @@ def test_base_bev_backbone_small(golden_dir):
     with torch.no_grad():
         y = nets.base_bev_backbone(g["x"], sd, "bb", g["cfg"])
     torch.testing.assert_close(y[:, ::4], g["y_s"], rtol=1e-4, atol=1e-4)
+
+
+def test_lss_geometry_and_pool(golden_dir):
+    from oracle import lss
+    g = _load(golden_dir, "lss_small.pt")
+    cfg = g["cfg"]
+    fr = lss.create_frustum(cfg["grid_conf"], cfg["data_aug_conf"]["final_dim"], cfg["img_downsample"])
+    geom = lss.get_geometry(fr, g["rots"], g["trans"], g["intrins"], g["post_rots"], g["post_trans"])
+    torch.testing.assert_close(geom, g["geom"], rtol=0, atol=0)
+    dx, bx, nx = lss.gen_dx_bx(cfg["grid_conf"]["xbound"], cfg["grid_conf"]["ybound"], cfg["grid_conf"]["zbound"])
+    B, N = g["trans"].shape[:2]
+    D, fH, fW, _ = fr.shape
+    x = lss.outer_product(g["depth_logits"], g["feat"]).view(B, N, -1, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    bev = lss.voxel_pooling(geom, x, dx, bx, nx, exact=False)
+    torch.testing.assert_close(bev, g["bev"], rtol=1e-5, atol=1e-5)          # faithful cumsum-trick restatement
+    bev_exact = lss.voxel_pooling(geom, x, dx, bx, nx, exact=True)
+    torch.testing.assert_close(bev_exact, g["bev"], rtol=1e-3, atol=1e-4)    # the trick's own cancellation noise
