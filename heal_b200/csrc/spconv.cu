@@ -290,13 +290,13 @@ extern "C" int heal_spconv_build_table(const int* coords, const int* num_rows_de
 }
 
 extern "C" int heal_spconv_subm_neighbors(const int* coords, const int* num_rows_dev, int capacity, const int* spatial_shape3_host,
-                                          const int* ksize3_host, const uint32_t* table_keys, const int* table_vals,
+                                          const int* ksize3_host, const uint32_t* table_keys, const int* table_vals, int table_capacity,
                                           int* nbr_out, void* stream_) {
     if (!coords || !table_keys || !table_vals || !nbr_out || capacity < 1) return HEAL_ERR_ARG;
     KShape ks; ks.kz = ksize3_host[0]; ks.ky = ksize3_host[1]; ks.kx = ksize3_host[2];
     ks.sz = ks.sy = ks.sx = 1; ks.pz = ks.py = ks.px = 0;
     int K = ks.kz * ks.ky * ks.kx;
-    SpGeom g = make_geom(spatial_shape3_host, table_log2(capacity));
+    SpGeom g = make_geom(spatial_shape3_host, table_log2(table_capacity));
     long long total = (long long)capacity * K;
     k_sp_subm_nbr<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)coords, num_rows_dev, capacity, g, ks,
                                                                                      table_keys, table_vals, nbr_out);

@@ -565,13 +565,14 @@ class SparseTensor:
     """feats (cap,C) f32 | None, coords (cap,4) i32 [b,z,y,x], rows_dev (1,) i32 device count or None (= cap rows live),
     spatial_shape [Z,Y,X], batch.  `table` (keys, vals) maps a site to its row (built on demand)."""
 
-    def __init__(self, feats, coords, rows_dev, spatial_shape, batch, table=None):
+    def __init__(self, feats, coords, rows_dev, spatial_shape, batch, table=None, table_capacity=None):
         self.feats, self.coords, self.rows_dev = feats, coords, rows_dev
         self.spatial_shape, self.batch, self.table = [int(v) for v in spatial_shape], int(batch), table
         self.capacity = coords.shape[0]
+        self.table_capacity = table_capacity if table_capacity is not None else self.capacity
 
     def with_feats(self, feats):
-        return SparseTensor(feats, self.coords, self.rows_dev, self.spatial_shape, self.batch, self.table)
+        return SparseTensor(feats, self.coords, self.rows_dev, self.spatial_shape, self.batch, self.table, self.table_capacity)
 
     def dense(self):
         """(B, C, D, H, W) like spconv's SparseConvTensor.dense() (test / API helper; one host sync)."""
@@ -602,7 +603,7 @@ def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
     nbr = torch.empty((st.capacity, K), dtype=torch.int32, device=st.coords.device)
     with _Prof("spconv_rulebook"):
         rc = lib.heal_spconv_subm_neighbors(_p(st.coords), _p(st.rows_dev), st.capacity, _host_i32(st.spatial_shape),
-                                            _host_i32(ksize), _p(keys), _p(vals), _p(nbr), _stream())
+                                            _host_i32(ksize), _p(keys), _p(vals), st.table_capacity, _p(nbr), _stream())
     check(rc, "heal_spconv_subm_neighbors")
     return nbr
 
@@ -630,7 +631,9 @@ def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int]
                                               _host_i32(ksize), _host_i32(stride), _host_i32(pad), out_capacity,
                                               _p(ocoords), _p(orows), _p(okeys), _p(ovals), _p(nbr), _p(ws), ws.numel(), _stream())
     check(rc, "heal_spconv_strided_rulebook")
-    return SparseTensor(None, ocoords, orows, oshape, st.batch, (okeys, ovals)), nbr
+    # one host sync per strided layer (spconv does the same) so that worst-case capacities do not compound level to level
+    m = min(int(orows.item()), out_capacity)
+    return SparseTensor(None, ocoords[:m], None, oshape, st.batch, (okeys, ovals), table_capacity=out_capacity), nbr[:m]
 
 
 def sp_gather_gemm(feats: torch.Tensor, nbr: torch.Tensor, rows_dev, weight: torch.Tensor, bias, relu: bool) -> torch.Tensor:

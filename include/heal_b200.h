@@ -159,7 +159,8 @@ int heal_lss_pool(const float* depth_logits, const float* feat, const int* cell,
  * (keys u32, vals i32, heal_spconv_table_size(capacity) entries each) maps a site to its row.
  * Rulebooks are output-stationary: nbr[row][k] = input row under kernel offset k (z-major, then y, x) or -1.
  *  - build_table          site -> row map of an existing tensor (first level, from the voxelizer's coords)
- *  - subm_neighbors       SubMConv3d rulebook (output sites = input sites), shared by every conv with the same indice_key
+ *  - subm_neighbors       SubMConv3d rulebook (output sites = input sites), shared by every conv with the same indice_key;
+ *                         table_capacity = the capacity the table was built with (its size = heal_spconv_table_size of it)
  *  - strided_rulebook     SparseConv3d: output sites (deterministic order), their table, and the rulebook
  *  - gather_gemm          out[r] = act(bias + sum_k in[nbr[r][k]] . W[k]),  W fp32 [kvol][Cin][Cout] with BN folded
  *  - sparse_to_bev        .dense() + view(N, C*D, H, W): bev_out (B,H,W,C*D) channels-last fp32, pre-zeroed, channel = c*D+z */
@@ -167,7 +168,7 @@ size_t heal_spconv_table_size(int capacity);
 int heal_spconv_build_table(const int* coords, const int* num_rows_dev, int capacity, const int* spatial_shape3_host, int batch,
                             uint32_t* table_keys, int* table_vals, void* stream);
 int heal_spconv_subm_neighbors(const int* coords, const int* num_rows_dev, int capacity, const int* spatial_shape3_host,
-                               const int* ksize3_host, const uint32_t* table_keys, const int* table_vals,
+                               const int* ksize3_host, const uint32_t* table_keys, const int* table_vals, int table_capacity,
                                int* nbr_out, void* stream);
 size_t heal_spconv_strided_workspace(int in_capacity, int out_capacity, int kvol);
 int heal_spconv_strided_rulebook(const int* in_coords, const int* in_rows_dev, int in_capacity,

@@ -53,10 +53,10 @@ def test_strided_conv_vs_oracle(ksize, stride, pad, shape):
     st = ops.SparseTensor(feats.cuda(), torch.from_numpy(coords).cuda(), None, shape, B)
     out_st, nbr = ops.sp_strided(st, ksize, stride, pad)
     assert out_st.spatial_shape == oshape
-    m = int(out_st.rows_dev.item())
+    m = out_st.capacity
     assert m == len(rc)                                           # same active output set size
     wp = w.reshape(cout, K, cin).permute(1, 2, 0).contiguous().cuda()
-    out = ops.sp_gather_gemm(st.feats, nbr, out_st.rows_dev, wp, None, False)[:m].cpu()
+    out = ops.sp_gather_gemm(st.feats, nbr, None, wp, None, False)[:m].cpu()
     oc = out_st.coords[:m].cpu().numpy()
     order = np.argsort(_lin(oc, oshape))
     assert np.array_equal(oc[order], rc)                          # identical site set (oracle order = sorted)
