@@ -38,6 +38,21 @@ def small_model_args():
     }
 
 
+def baseline_att_args(core_method="point_pillar", encoder_args=None, inplanes=64, strides=(2, 2, 2)):
+    enc = encoder_args or {"voxel_size": VOXEL, "lidar_range": SMALL_RANGE,
+                           "pillar_vfe": {"use_norm": True, "with_distance": False, "use_absolute_xyz": True, "num_filters": [64]},
+                           "point_pillar_scatter": {"num_features": 64}}
+    return {
+        "lidar_range": SMALL_RANGE, "ego_modality": "m1",
+        "m1": {"core_method": core_method, "sensor_type": "lidar", "encoder_args": enc,
+               "backbone_args": {"layer_nums": [3, 5, 8], "layer_strides": list(strides), "num_filters": [64, 128, 256],
+                                 "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128], "inplanes": inplanes},
+               "shrink_header": {"kernal_size": [3], "stride": [1], "padding": [1], "dim": [256], "input_dim": 384}},
+        "fusion_method": "att", "att": {"feat_dim": 256},
+        "in_head": 256, "anchor_number": 2, "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]},
+    }
+
+
 def lss_small_cfg():
     return {"grid_conf": {"xbound": [-12.8, 12.8, 0.4], "ybound": [-12.8, 12.8, 0.4], "zbound": [-10, 10, 20.0],
                           "ddiscr": [2, 30, 16], "mode": "LID"},
@@ -152,6 +167,18 @@ def main():
     torch.save({"cfg": lcfg, "rots": rots, "trans": trans, "intrins": intr, "post_rots": post_rots, "post_trans": post_trans,
                 "depth_logits": depth_logits, "feat": feat, "geom": geom, "bev": bev}, os.path.join(OUT, "lss_small.pt"))
     print("lss_small:", tuple(geom.shape), tuple(bev.shape), float(bev.abs().max()))
+    # ---- 5. HeterModelBaseline + AttFusion (C3 family; PointPillar encoder so that the reference runs without spconv) ----
+    from opencood.models.heter_model_baseline import HeterModelBaseline
+    bargs = baseline_att_args()
+    bm = HeterModelBaseline(copy.deepcopy(bargs)).eval()
+    bshapes2 = procedural.shapes_of(bm)
+    bm.load_state_dict(procedural.make_state_dict(bshapes2), strict=True)
+    with torch.no_grad():
+        bout = bm(copy.deepcopy(data))
+    torch.save({"args": bargs, "shapes": bshapes2, "data": data,
+                "out": {k: bout[k] for k in ("cls_preds", "reg_preds", "dir_preds")}},
+               os.path.join(OUT, "heter_model_baseline_att_small.pt"))
+    print("heter_model_baseline_att_small:", {k: tuple(v.shape) for k, v in bout.items() if torch.is_tensor(v)})
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

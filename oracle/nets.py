@@ -354,3 +354,36 @@ def randomize_bn_(sd_or_module, seed=1234):
             sd[base + "weight"].copy_(torch.rand(v.shape, generator=g) + 0.5)
             sd[base + "bias"].copy_(torch.randn(v.shape, generator=g) * 0.1)
     return sd
+
+
+def heter_model_baseline(sd: SD, args, data_dict, encoder_fns=None):
+    """heter_model_baseline.py:155-236 with fusion_method 'att': encoder -> BaseBEVBackbone -> per-agent shrinker ->
+    AttFusion -> (shrink) -> heads.  `encoder_fns[m](data_dict, m)` may supply the encoder output (SECOND / camera)."""
+    mods = [k for k in args.keys() if k.startswith("m") and k[1:].isdigit()]
+    rng = args["lidar_range"]
+    H, W = rng[4] - rng[1], rng[3] - rng[0]
+    affine = normalize_pairwise_tfm(data_dict["pairwise_t_matrix"], H, W, 1)
+    aml = data_dict["agent_modality_list"]
+    cnt = Counter(aml)
+    feats = {}
+    for m in mods:
+        if m not in cnt:
+            continue
+        if encoder_fns is not None and m in encoder_fns:
+            f = encoder_fns[m](data_dict, m)
+        else:
+            f = point_pillar_encoder(sd, f"encoder_{m}", args[m]["encoder_args"], data_dict[f"inputs_{m}"])
+        f = base_bev_backbone(f, sd, f"backbone_{m}", args[m]["backbone_args"])
+        feats[m] = downsample_conv(f, sd, f"shrinker_{m}", args[m]["shrink_header"])
+    counting = {m: 0 for m in mods}
+    lst = []
+    for m in aml:
+        lst.append(feats[m][counting[m]])
+        counting[m] += 1
+    x = torch.stack(lst)
+    assert args["fusion_method"] == "att"
+    fused = att_fusion(x, data_dict["record_len"], affine)
+    if "shrink_header" in args:
+        fused = downsample_conv(fused, sd, "shrink_conv", args["shrink_header"])
+    return {"cls_preds": conv(fused, sd, "cls_head"), "reg_preds": conv(fused, sd, "reg_head"),
+            "dir_preds": conv(fused, sd, "dir_head"), "fused_feature": fused}

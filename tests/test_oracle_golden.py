@@ -69,3 +69,12 @@ def test_lss_geometry_and_pool(golden_dir):
     torch.testing.assert_close(bev, g["bev"], rtol=1e-5, atol=1e-5)          # faithful cumsum-trick restatement
     bev_exact = lss.voxel_pooling(geom, x, dx, bx, nx, exact=True)
     torch.testing.assert_close(bev_exact, g["bev"], rtol=1e-3, atol=1e-4)    # the trick's own cancellation noise
+
+
+def test_heter_model_baseline_att_small(golden_dir):
+    g = _load(golden_dir, "heter_model_baseline_att_small.pt")
+    sd = procedural.make_state_dict(g["shapes"])
+    with torch.no_grad():
+        out = nets.heter_model_baseline(sd, g["args"], g["data"])
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        torch.testing.assert_close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
