@@ -103,3 +103,20 @@ def test_submodule_api_shapes():
     pf = PyramidFusion(make_golden.small_model_args()["fusion_backbone"]).eval().cuda()
     f, occ = pf.forward_single(y)
     assert f.shape == (2, 384, 16, 24) and [o.shape for o in occ] == [(2, 1, 16, 24), (2, 1, 8, 12), (2, 1, 4, 6)]
+
+
+def test_agent_sharded_world1_equals_plain_forward():
+    """forward_agent_sharded (pack -> gather -> unpack -> fuse tail) on one rank == the plain module forward."""
+    from heal_b200 import synth, parallel
+    args = make_golden.small_model_args()
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "heter_pyramid_collab_small.pt"), weights_only=False)
+    model, _ = _build(args, g["shapes"])
+    sc = synth.scene(5, n_agents=3, rings=16, azimuth=256)
+    offs = np.concatenate([[0], np.cumsum([p.shape[0] for p in sc["points"]])]).astype(np.int32)
+    data = {"inputs_m1": {"points": torch.from_numpy(np.concatenate(sc["points"])).cuda(), "agent_offsets": torch.from_numpy(offs).cuda()},
+            "agent_modality_list": ["m1"] * 3, "record_len": torch.tensor([3]), "pairwise_t_matrix": torch.from_numpy(sc["pairwise_t_matrix"]).cuda()}
+    with torch.no_grad():
+        a = model(data)
+        b = parallel.forward_agent_sharded(model, data, 0, 1)
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        torch.testing.assert_close(a[k], b[k], rtol=0, atol=0)

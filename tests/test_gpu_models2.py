@@ -121,8 +121,8 @@ def test_c4_lss_plus_pointpillar_hetero_vs_oracle(prec, tol):
     engine.set_precision(prec)
     args = make_golden.small_model_args()                  # lidar +-12.8 -> 64x64 pillars, fusion at 32x32
     lcfg = make_golden.lss_small_cfg()
-    lcfg["grid_conf"]["xbound"] = [-6.4, 6.4, 0.2]         # camera grid = half the lidar range -> 64x64 @0.2, padded x2
-    lcfg["grid_conf"]["ybound"] = [-6.4, 6.4, 0.2]
+    lcfg["grid_conf"]["xbound"] = [-6.4, 6.4, 0.4]         # camera grid = half the lidar range -> 32x32 @0.4, zero-padded x2
+    lcfg["grid_conf"]["ybound"] = [-6.4, 6.4, 0.4]
     lcfg["img_features"] = 64
     args["m2"] = {"core_method": "lift_splat_shoot", "sensor_type": "camera", "encoder_args": lcfg,
                   "camera_mask_args": {"grid_conf": lcfg["grid_conf"]},
