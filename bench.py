@@ -240,7 +240,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        os.environ["NCCL_DEBUG"] = os.environ.get("HEAL_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from heal_b200._lib import lib
     from heal_b200 import ops, engine
     from heal_b200.models.heter_pyramid_collab import HeterPyramidCollab
@@ -254,7 +256,8 @@ def main():
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
 
-    scenes = build_scenes(4, n_agents, seed0=100 + 10 * rank)
+    # replicas: every rank has its own scene stream; agent-sharded: all ranks work on the SAME scenes
+    scenes = build_scenes(4, n_agents, seed0=100 + (10 * rank if opt.parallelism == "scene" else 0))
     dev_scenes, host_scenes = [], []
     for sc in scenes:
         hp = torch.from_numpy(sc["points"]).pin_memory()
