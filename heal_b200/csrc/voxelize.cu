@@ -43,6 +43,8 @@ __global__ void k_cells_insert(const float4* __restrict__ pts, const int* __rest
                                uint32_t* __restrict__ keys, int* __restrict__ firsts, int* __restrict__ pt_slot) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.P) return;
+    // `P` may be the CAPACITY of a static (CUDA-graph) input buffer: the live point count is offs[A] on the device
+    if (i >= offs[c.A]) { pt_slot[i] = -1; return; }
     float4 p = __ldg(pts + i);
     // IEEE fp32 subtract + divide + floor, exactly as the CPU generator (no reciprocal multiply).
     float fx = floorf(__fdiv_rn(__fsub_rn(p.x, c.minx), c.vsx));

@@ -33,12 +33,14 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def forward_nhwc(self, x):
+    out_channels = property(lambda self: self.conv2.out_channels)
+
+    def forward_nhwc(self, x, out=None):
         idt = x
         if self.downsample is not None:
             idt = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
         y = conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        return conv_bn_act(y, self.conv2, self.bn2, relu=True, residual=idt)
+        return conv_bn_act(y, self.conv2, self.bn2, relu=True, residual=idt, out=out)
 
 
 class Bottleneck(nn.Module):
@@ -57,13 +59,15 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def forward_nhwc(self, x):
+    out_channels = property(lambda self: self.conv3.out_channels)
+
+    def forward_nhwc(self, x, out=None):
         idt = x
         if self.downsample is not None:
             idt = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
         y = conv_bn_act(x, self.conv1, self.bn1, relu=True)
         y = conv_bn_act(y, self.conv2, self.bn2, relu=True)
-        return conv_bn_act(y, self.conv3, self.bn3, relu=True, residual=idt)
+        return conv_bn_act(y, self.conv3, self.bn3, relu=True, residual=idt, out=out)
 
 
 class ResNetModified(nn.Module):
@@ -95,11 +99,33 @@ class ResNetModified(nn.Module):
             seq.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width))
         return nn.Sequential(*seq)
 
+    # A level whose largest per-layer tensor (all images) exceeds this is run image by image ("agent-major"): each agent
+    # goes through the whole level before the next one starts, so that its intermediates (<= 34 MB at 256x256) stay
+    # resident in the 126 MB L2 between producer and consumer instead of round-tripping HBM.
+    AGENT_MAJOR_BYTES = 48 << 20
+
+    def _run_level(self, layer, x):
+        blocks = list(layer)
+        stride = blocks[0].stride
+        Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
+        widest = max(max(getattr(b, "conv1").out_channels, b.out_channels) for b in blocks)
+        biggest = x.N * max(x.H * x.W * max(x.C, blocks[0].conv1.out_channels), Ho * Wo * widest) * 4
+        if x.N == 1 or biggest <= self.AGENT_MAJOR_BYTES:
+            for blk in blocks:
+                x = blk.forward_nhwc(x)
+            return x
+        from ...engine import act_fmt
+        out = ops.act_empty(x.N, Ho, Wo, blocks[-1].out_channels, act_fmt(), x.device)
+        for a in range(x.N):
+            xi = x.image(a)
+            for j, blk in enumerate(blocks):
+                xi = blk.forward_nhwc(xi, out=out.image(a) if j == len(blocks) - 1 else None)
+        return out
+
     def forward_nhwc(self, x):
         feats = []
         for i in range(self.layernum):
-            for blk in getattr(self, f"layer{i}"):
-                x = blk.forward_nhwc(x)
+            x = self._run_level(getattr(self, f"layer{i}"), x)
             feats.append(x)
         return feats
 
