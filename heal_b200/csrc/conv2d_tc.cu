@@ -132,6 +132,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp; the compiler keeps code under this predicate on the uniform datapath (the tcgen05 /
+// TMA instructions take uniform-register operands: issuing them from an `if (lane == 0)` region instead costs an
+// ELECT + branch loop per instruction, measured at ~110 cycles per tcgen05.mma).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n .reg .b32 rx;\n .reg .pred px;\n elect.sync rx|px, 0xffffffff;\n @px mov.s32 %0, 1;\n}" : "+r"(pred));
+    return pred;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -174,8 +183,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int kblocks = p.taps * kcn;
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
-        if (lane == 0) {
+        // ============================== TMA producer (whole warp loops, one elected lane issues) ==
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -189,16 +198,19 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     const bool ldA = !(p.dbg & 4), ldB = !(p.dbg & 2);
-                    mbar_expect_tx(bar_full + 8 * stage, (uint32_t)((ldA ? p.planes * A_TILE_BYTES : 0) + (ldB ? p.planes * B_TILE_BYTES : 0)));
-                    if (ldA) tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, img, 0);
-                    if (ldB) tma_load_3d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * stage, (uint32_t)((ldA ? p.planes * A_TILE_BYTES : 0) + (ldB ? p.planes * B_TILE_BYTES : 0)));
+                        if (ldA) tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, img, 0);
+                        if (ldB) tma_load_3d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ================================
-        if (lane == 0) {
+        // ============================== MMA issuer (whole warp loops, one elected lane issues) ====
+        {
             // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -215,6 +227,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
                     const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES), b_lo = umma_desc_sw128(sb + B_TILE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per 16-element K step
@@ -244,9 +257,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     umma_commit(bar_empty + 8 * stage);       // smem slot free once these MMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);             // accumulator ready for the epilogue
+                if (elect_one()) umma_commit(bar_tfull + 8 * acc);   // accumulator ready for the epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
