@@ -44,6 +44,7 @@ struct TcP {
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
     int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads
     const float* bias;            // [Cout]
     // residual (optional): split planes or fp32
@@ -141,20 +142,37 @@ __device__ __forceinline__ uint32_t elect_one() {
     return pred;
 }
 
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int BLOCK_N, int STAGES>
+// STG = number of 64-channel output staging buffers in shared memory (0: the epilogue stores straight to global memory;
+// >0: it writes the swizzled tile to smem and one elected thread issues a TMA tensor store, so every global write is a
+// full coalesced line and the drain is asynchronous).
+template <int BLOCK_N, int STAGES, int STG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
+k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const TcP p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024 B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     const int stage_bytes = p.planes * (A_TILE_BYTES + B_TILE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+    const int stg_bytes = p.planes * A_TILE_BYTES;                        // one staging buffer: [plane][128 rows][128 B]
+    uint8_t* stg = smem + (size_t)STAGES * stage_bytes;                   // 1024-aligned (stage_bytes is a multiple of 1024)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
@@ -273,6 +291,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row = quarter * 32 + lane;            // accumulator row = pixel within the tile
         constexpr int CHUNK = (BLOCK_N >= 32) ? 32 : 16;
         int acc = 0; uint32_t acc_phase = 0;
+        int stg_count = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
@@ -285,6 +304,76 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const size_t pix = ((size_t)img * (p.Ho * p.up) + (size_t)(oh * p.up + ui)) * (size_t)(p.Wo * p.up) + (size_t)(ow * p.up + uj);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
+            if constexpr (STG > 0 && BLOCK_N >= 64) {
+              if (p.tma_out) {
+                const uint32_t stg_base = smem_u32(stg);
+#pragma unroll 1
+                for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
+                    const int b = stg_count % STG;
+                    // (A) buffer b is free once at most STG-1 store groups are still reading shared memory
+                    if (warp == 2 && lane == 0) bulk_wait_read<STG - 1>();
+                    epi_bar(1);
+                    // (B) this warp's 32 columns of the 64-column chunk -> registers -> epilogue -> swizzled smem
+                    uint32_t raw[32];
+                    const int col0 = c64 * 64 + chalf * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col0), raw);
+                    tmem_wait_ld();
+                    const uint32_t srow = stg_base + b * stg_bytes + row * 128;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int c = ch0 + col0 + g8 * 8;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
+                        if (valid && c + 8 <= p.Cout) {
+                            if (p.res_split) {
+                                const __nv_bfloat16* rp = p.res_split + pix * p.res_cs + p.res_co + c;
+                                uint4 h = __ldg(reinterpret_cast<const uint4*>(rp));
+                                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
+                                if (p.planes == 2) {
+                                    uint4 l = __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane));
+                                    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
+                                }
+                            } else if (p.res_f32) {
+                                const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        float lo[8];
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { hw[j] = pack_bf16(v[2 * j], v[2 * j + 1]); lw[j] = pack_bf16(lo[2 * j], lo[2 * j + 1]); }
+                        const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk16), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+                        if (p.planes == 2)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + A_TILE_BYTES + chunk16), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+                    }
+                    fence_async_smem();
+                    epi_bar(2);
+                    // (C) one thread drains the buffer with a TMA tensor store (out-of-range pixels are clipped by the unit)
+                    if (warp == 2 && lane == 0 && !(p.dbg & 1)) {
+                        tma_store_5d(&tmO, stg_base + b * stg_bytes, ch0 + c64 * 64, tw_i * p.TW, th_i * p.TH, img, 0);
+                        bulk_commit();
+                    }
+                    ++stg_count;
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+              }
+            }
 #pragma unroll 1
             for (int cc = chalf; cc < BLOCK_N / CHUNK; cc += 2) {
                 uint32_t raw[CHUNK];
@@ -365,6 +454,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_arrive(bar_tempty + 8 * acc);          // 128 arrivals release this accumulator buffer
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (STG > 0 && warp == 2 && lane == 0) bulk_wait_all();     // all output tiles have left shared memory
+        (void)stg_count;
     }
     tc_fence_before();
     __syncthreads();
@@ -389,18 +480,19 @@ PFN_tmEncodeTiled get_encode() {
     return fn;
 }
 
-template <int BLOCK_N, int STAGES>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& p, cudaStream_t st) {
-    size_t smem = 1024 + (size_t)STAGES * p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + 256;
+template <int BLOCK_N, int STAGES, int STG>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TcP& p, cudaStream_t st) {
+    size_t smem = 1024 + (size_t)STAGES * p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + (size_t)STG * p.planes * A_TILE_BYTES + 256;
+    if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_conv2d_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_conv2d_tc<BLOCK_N, STAGES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return HEAL_ERR_LAUNCH;
         attr_set = true;
     }
     int total = p.m_tiles * p.n_tiles;
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
-    k_conv2d_tc<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, p);
     return heal_check_launch();
 }
 
@@ -467,11 +559,35 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
     }
+    // output tensor map for the TMA-store epilogue (split / bf16 output at conv resolution, 64-channel boxes)
+    CUtensorMap tmO = tmA;
+    p.tma_out = 0;
+    {
+        const char* e = getenv("HEAL_TC_TMA_STORE");
+        const bool want = !(e && atoi(e) == 0);
+        if (want && out_split && upsample == 1 && block_n >= 64 && (Cout % 64) == 0 && !(out_cstride & 7) && !(out_coffset & 7) &&
+            (!res_split || (!(res_cstride & 7) && !(res_coffset & 7)))) {
+            cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N, (cuuint64_t)planes};
+            cuuint64_t strides[4] = {(cuuint64_t)out_cstride * 2, (cuuint64_t)Wo * out_cstride * 2, (cuuint64_t)Ho * Wo * out_cstride * 2,
+                                     (cuuint64_t)out_plane_stride * 2};
+            if (planes == 1) strides[3] = strides[2] * N;
+            cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1u, (cuuint32_t)planes};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            void* base = (void*)((__nv_bfloat16*)out_split + out_coffset);
+            CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
+            p.tma_out = out_f32 ? 0 : 1;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream_;
+    const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
     switch (block_n) {
-        case 16: return launch_tc<16, 4>(tmA, tmB, p, st);
-        case 32: return launch_tc<32, 4>(tmA, tmB, p, st);
-        case 64: return launch_tc<64, 4>(tmA, tmB, p, st);
-        default: return launch_tc<128, 3>(tmA, tmB, p, st);
+        case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, p, st);
+        case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, p, st);
+        case 64: return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, p, st);
+        default:
+            if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, p, st);
+            return kblocks <= 4 ? launch_tc<128, 2, 2>(tmA, tmB, tmO, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, p, st);
     }
 }
