@@ -347,6 +347,9 @@ def main():
         # ---- instrumented pass: per-kernel-family device time (events around every C-ABI conv call) ----
         prof = None
         if rank == 0:
+            for k in range(2):                     # un-instrumented eager warm-up (allocator pools differ from the graph's)
+                frame_dev(k, eager=True)
+            torch.cuda.synchronize()
             ops.PROFILE = []
             for k in range(2):
                 frame_dev(k, eager=True)
