@@ -44,6 +44,7 @@ struct TcP {
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
     int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads
     const float* bias;            // [Cout]
@@ -86,6 +87,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
                  " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
                  " [%0], [%1, {%3, %4, %5}], [%2];"
@@ -101,6 +107,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
     return d;
+}
+
+// Same, for a start address that is only 128 B aligned (a row offset inside a swizzled tile): the descriptor's
+// base-offset field carries the swizzle phase (address bits [7,10)) of the first row.
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr) {
+    return umma_desc_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -169,7 +181,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // 1024 B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
-    const int stage_bytes = p.planes * (A_TILE_BYTES + B_TILE_BYTES);
+    // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
+    const int halo_a_plane = (p.TW + 2) * 128;
+    const int halo_a_bytes = (p.planes * halo_a_plane + 1023) & ~1023;
+    const int stage_bytes = p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES);
     const int stg_bytes = p.planes * A_TILE_BYTES;                        // one staging buffer: [plane][128 rows][128 B]
     uint8_t* stg = smem + (size_t)STAGES * stage_bytes;                   // 1024-aligned (stage_bytes is a multiple of 1024)
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
@@ -198,7 +213,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int kcn = p.blockdiag ? 1 : p.kc_blocks;      // channel blocks per tap visited by one tile
-    const int kblocks = p.taps * kcn;
+    const int kblocks = (p.halo ? 3 : p.taps) * kcn;    // halo mode: one k-block per kernel ROW (3 taps each)
 
     if (warp == 0) {
         // ============================== TMA producer (whole warp loops, one elected lane issues) ==
@@ -213,6 +228,18 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const int tap = kb / kcn, kc = p.blockdiag ? nt : kb % kcn;
                     const int r = tap / p.taps_w, s = tap % p.taps_w;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (p.halo) {
+                        // k-block = (kernel row tap, channel block): pixels [w0-1, w0+TW] of input row h0+tap-1, and the 3 taps' weights
+                        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + 3 * B_TILE_BYTES)));
+                            tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 - 1, h0 + tap - 1, img, 0);
+                            tma_load_4d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, nt * BLOCK_N, tap * 3, 0);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     const bool ldA = !(p.dbg & 4), ldB = !(p.dbg & 2);
@@ -241,6 +268,48 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
+                    if (p.halo) {
+                        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int s = 0; s < 3; ++s) {
+                                // tap s reads rows [s, s+128) of the halo tile: start address + s*128 B, swizzle phase in base_offset
+                                const uint32_t ah = sa + s * 128, al = ah + halo_a_plane;
+                                const uint32_t bh = sb + s * B_TILE_BYTES, bl = bh + 3 * B_TILE_BYTES;
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                    const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32), a_lo = umma_desc_sw128_off(al + k * 32);
+                                    if (p.blockdiag) {
+                                        const uint32_t bo = k * 16 * 128 + k * 32;
+                                        const uint64_t b_hi = umma_desc_sw128(bh + bo), b_lo = umma_desc_sw128(bl + bo);
+                                        const uint32_t td = tmem_d + (uint32_t)(k * 16);
+                                        const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
+                                        if (p.planes == 2) {
+                                            umma_bf16(td, a_lo, b_hi, idesc16, f0);
+                                            umma_bf16(td, a_hi, b_lo, idesc16, 1u);
+                                            umma_bf16(td, a_hi, b_hi, idesc16, 1u);
+                                        } else {
+                                            umma_bf16(td, a_hi, b_hi, idesc16, f0);
+                                        }
+                                    } else {
+                                        const uint64_t b_hi = umma_desc_sw128(bh + k * 32), b_lo = umma_desc_sw128(bl + k * 32);
+                                        const uint32_t first = (kb == 0 && s == 0 && k == 0) ? 0u : 1u;
+                                        if (p.planes == 2) {
+                                            umma_bf16(tmem_d, a_lo, b_hi, idesc, first);
+                                            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                                            umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+                                        } else {
+                                            umma_bf16(tmem_d, a_hi, b_hi, idesc, first);
+                                        }
+                                    }
+                                }
+                            }
+                            umma_commit(bar_empty + 8 * stage);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
@@ -482,7 +551,9 @@ PFN_tmEncodeTiled get_encode() {
 
 template <int BLOCK_N, int STAGES, int STG>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TcP& p, cudaStream_t st) {
-    size_t smem = 1024 + (size_t)STAGES * p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + (size_t)STG * p.planes * A_TILE_BYTES + 256;
+    size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2);
+    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2;
+    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -536,12 +607,18 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     p.out_split = (__nv_bfloat16*)out_split; p.out_plane = out_plane_stride; p.out_cs = out_cstride; p.out_co = out_coffset;
     p.out_f32 = out_f32; p.out32_cs = out32_cstride; p.out32_co = out32_coffset;
 
+    {
+        const char* e = getenv("HEAL_TC_HALO");
+        const bool want = !(e && atoi(e) == 0);
+        p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
+    }
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)planes};
         cuuint64_t strides[4] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)W * in_cstride * 2, (cuuint64_t)H * W * in_cstride * 2,
                                  (cuuint64_t)in_plane_stride * 2};
         cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), 1u, (cuuint32_t)planes};
+        if (p.halo) box[1] = (cuuint32_t)(p.TW + 2);
         cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
         void* base = (void*)((const __nv_bfloat16*)in_split + in_coffset);
         if (planes == 1) { strides[3] = strides[2] * N; }
@@ -555,8 +632,19 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         cuuint64_t strides[2] = {wk * 2, (cuuint64_t)w_rows * wk * 2};
         cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, (cuuint32_t)planes};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r;
+        if (p.halo) {
+            // {K, coutp, taps, plane}: one box brings the 3 horizontal taps of a kernel row
+            cuuint64_t d4[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)taps, (cuuint64_t)planes};
+            cuuint64_t s4[3] = {wk * 2, (cuuint64_t)coutp * wk * 2, (cuuint64_t)w_rows * wk * 2};
+            cuuint32_t b4[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, 3u, (cuuint32_t)planes};
+            cuuint32_t e4[4] = {1, 1, 1, 1};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
     }
     // output tensor map for the TMA-store epilogue (split / bf16 output at conv resolution, 64-channel boxes)
@@ -585,7 +673,9 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     switch (block_n) {
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, p, st);
-        case 64: return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, p, st);
+        case 64:
+            if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, p, st);
+            return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, p, st);
         default:
             if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, p, st);
             return kblocks <= 4 ? launch_tc<128, 2, 2>(tmA, tmB, tmO, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, p, st);

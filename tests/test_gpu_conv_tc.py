@@ -112,6 +112,12 @@ STRIDE_GROUP_CASES = [
     ("g32_cg8_s2", 1, 256, 32, 64, 256, 3, 2, 1, 32),
     ("g32_cg16_s1", 1, 512, 16, 16, 512, 3, 1, 1, 32),
     ("g32_cg16_s2", 1, 512, 17, 23, 512, 3, 2, 1, 32),
+    # one-row tiles (W >= 128): halo loads (one activation box per kernel row, base-offset descriptors)
+    ("halo_res_w256", 2, 64, 5, 256, 64, 3, 1, 1, 1),
+    ("halo_res_cin128_w128", 1, 128, 7, 128, 64, 3, 1, 1, 1),
+    ("halo_ragged_w150", 1, 64, 4, 150, 64, 3, 1, 1, 1),
+    ("halo_g32_cg4_w128", 1, 128, 6, 128, 128, 3, 1, 1, 32),
+    ("halo_g32_cg8_w256", 1, 256, 3, 256, 256, 3, 1, 1, 32),
 ]
 
 
