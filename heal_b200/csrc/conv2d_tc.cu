@@ -44,6 +44,7 @@ struct TcP {
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
     int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads
@@ -109,10 +110,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-// Same, for a start address that is only 128 B aligned (a row offset inside a swizzled tile): the descriptor's
-// base-offset field carries the swizzle phase (address bits [7,10)) of the first row.
-__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr) {
-    return umma_desc_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
+// Same, for a start address that is only 128 B aligned (a ROW offset inside a TMA-written swizzled tile).
+// Measured on B200 (profiles/halo_diag.py): the tensor core applies the 128B swizzle to the ABSOLUTE shared-memory
+// address (bits [4,7) ^= bits [7,10)), exactly like the TMA unit, so a row-shifted view needs no base-offset:
+// the descriptor's base_offset field must stay 0 (setting it to the row phase produces garbage).
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, int mode) {
+    uint32_t ph = (saddr >> 7) & 7;
+    uint32_t bo = (mode == 0) ? 0u : ph;      // mode 1 kept only for the diagnostic script
+    return umma_desc_sw128(saddr) | ((uint64_t)bo << 49);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -278,7 +283,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 const uint32_t bh = sb + s * B_TILE_BYTES, bl = bh + 3 * B_TILE_BYTES;
 #pragma unroll
                                 for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                    const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32), a_lo = umma_desc_sw128_off(al + k * 32);
+                                    const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32, p.bo_mode), a_lo = umma_desc_sw128_off(al + k * 32, p.bo_mode);
                                     if (p.blockdiag) {
                                         const uint32_t bo = k * 16 * 128 + k * 32;
                                         const uint64_t b_hi = umma_desc_sw128(bh + bo), b_lo = umma_desc_sw128(bl + bo);
@@ -610,6 +615,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     {
         const char* e = getenv("HEAL_TC_HALO");
         const bool want = !(e && atoi(e) == 0);
+        { const char* b = getenv("HEAL_TC_BO"); p.bo_mode = b ? atoi(b) : 0; }
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
     }
     CUtensorMap tmA, tmB;
