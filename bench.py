@@ -139,7 +139,7 @@ def pick_host_threads():
     except Exception:
         pass
     cands = sorted({c for c in (8, 16, 32, 64, 128, avail) if c <= avail})
-    x = torch.randn(1, 64, 256, 256)
+    x = torch.randn(5, 64, 256, 256)          # the frame's most common conv shape (5 agents), enough work to use many threads
     w = torch.randn(64, 64, 3, 3)
     best, best_t = cands[0], float("inf")
     for c in cands:
@@ -223,15 +223,18 @@ def workload_config(n_gpus, parallelism, precision="tc32"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default 20 (5 for --impl reference: one CPU frame takes seconds)")
+    ap.add_argument("--warmup", type=int, default=None, help="default 3 (1 for --impl reference)")
     ap.add_argument("--impl", default="heal_b200")
     ap.add_argument("--parallelism", default="scene", choices=["scene", "agent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tc32", choices=["tc32", "bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     opt = ap.parse_args()
-    opt.warmup = max(opt.warmup, 3) if opt.impl != "reference" else opt.warmup
+    ref = opt.impl == "reference"
+    opt.steps = opt.steps if opt.steps is not None else (5 if ref else 20)
+    opt.warmup = opt.warmup if opt.warmup is not None else (1 if ref else 3)
+    opt.warmup = max(opt.warmup, 3) if not ref else opt.warmup
     if opt.impl == "reference":
         return run_reference(opt)
 
