@@ -28,7 +28,7 @@ SIGNATURES = {
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _ap, _vp]),
     "heal_conv2d_simt": (_i, [_ap, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _ap, _ap, _i, _i, _i,
                               _i, _i, _i, _i, _vp]),
-    "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i,
+    "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i,
                             _vp, _sz, _vp, _i, _i, _vp, _sz, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "heal_pyramid_fuse_level": (_i, [_ap, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ap, _vp]),
     "heal_att_fuse": (_i, [_ap, _vp, _i, _i, _i, _i, _ap, _vp]),

@@ -44,6 +44,7 @@ struct TcP {
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    int wstat;                    // grouped + halo: the n-tile's 16x16 diagonal weight sub-blocks (36 KiB) stay resident in smem
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
@@ -107,6 +108,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+// K-major, 32B-swizzled descriptor (rows of 32 B = 16 bf16, 8-row groups 256 B apart): the packed diagonal weight sub-blocks.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                           // SWIZZLE_32B
     return d;
 }
 
@@ -189,12 +201,16 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
     const int halo_a_plane = (p.TW + 2) * 128;
     const int halo_a_bytes = (p.planes * halo_a_plane + 1023) & ~1023;
-    const int stage_bytes = p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES);
+    const int stage_bytes = p.wstat ? halo_a_bytes
+                          : (p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES));
+    const int w_bytes = p.wstat ? p.planes * 9 * 2048 : 0;                // [plane][9 taps][64 rows][32 B] resident weights
     const int stg_bytes = p.planes * A_TILE_BYTES;                        // one staging buffer: [plane][128 rows][128 B]
-    uint8_t* stg = smem + (size_t)STAGES * stage_bytes;                   // 1024-aligned (stage_bytes is a multiple of 1024)
+    uint8_t* wreg = smem + (size_t)STAGES * stage_bytes;                  // 1024-aligned (stage_bytes is a multiple of 1024)
+    uint8_t* stg = wreg + w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], weights_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    const uint32_t bar_w = smem_u32(bars + 2 * STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
@@ -205,6 +221,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 256); }
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -224,6 +241,13 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ============================== TMA producer (whole warp loops, one elected lane issues) ==
         {
             int stage = 0; uint32_t phase = 0;
+            if (p.wstat) {          // gridDim.x is a multiple of n_tiles: this CTA keeps n-tile blockIdx.x % n_tiles for its whole life
+                if (elect_one()) {
+                    mbar_expect_tx(bar_w, (uint32_t)w_bytes);
+                    tma_load_4d(smem_u32(wreg), &tmB, bar_w, 0, (int)(blockIdx.x % p.n_tiles) * BLOCK_N, 0, 0);
+                }
+                __syncwarp();
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
@@ -237,9 +261,9 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // k-block = (kernel row tap, channel block): pixels [w0-1, w0+TW] of input row h0+tap-1, and the 3 taps' weights
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
                         if (elect_one()) {
-                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + 3 * B_TILE_BYTES)));
+                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + (p.wstat ? 0 : 3 * B_TILE_BYTES))));
                             tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 - 1, h0 + tap - 1, img, 0);
-                            tma_load_4d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, nt * BLOCK_N, tap * 3, 0);
+                            if (!p.wstat) tma_load_4d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, nt * BLOCK_N, tap * 3, 0);
                         }
                         __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -266,6 +290,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if (p.wstat) { mbar_wait(bar_w, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
@@ -286,7 +311,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32, p.bo_mode), a_lo = umma_desc_sw128_off(al + k * 32, p.bo_mode);
                                     if (p.blockdiag) {
                                         const uint32_t bo = k * 16 * 128 + k * 32;
-                                        const uint64_t b_hi = umma_desc_sw128(bh + bo), b_lo = umma_desc_sw128(bl + bo);
+                                        // resident weights: [plane][tap][sub-block k: 16 rows x 32 B]; tap = (kernel row kb) * 3 + s
+                                        const uint32_t ws = smem_u32(wreg) + (uint32_t)((kb * 3 + s) * 2048 + k * 512);
+                                        const uint64_t b_hi = p.wstat ? umma_desc_sw32(ws) : umma_desc_sw128(bh + bo);
+                                        const uint64_t b_lo = p.wstat ? umma_desc_sw32(ws + 9 * 2048) : umma_desc_sw128(bl + bo);
                                         const uint32_t td = tmem_d + (uint32_t)(k * 16);
                                         const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
                                         if (p.planes == 2) {
@@ -557,8 +585,8 @@ PFN_tmEncodeTiled get_encode() {
 template <int BLOCK_N, int STAGES, int STG>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TcP& p, cudaStream_t st) {
     size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2);
-    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2;
-    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
+    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (p.wstat ? 0 : (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2);
+    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (p.wstat ? (size_t)p.planes * 9 * 2048 : 0) + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -568,6 +596,8 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     }
     int total = p.m_tiles * p.n_tiles;
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
+    if (p.wstat) grid = (grid / p.n_tiles) * p.n_tiles;       // every CTA keeps one n-tile (its weights stay in shared memory)
+    if (grid < 1) return HEAL_ERR_UNSUPPORTED;
     k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, p);
     return heal_check_launch();
 }
@@ -575,7 +605,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
 }  // namespace
 
 extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
-                              const void* w_packed, int w_rows, int coutp, const float* bias,
+                              const void* w_packed, const void* w_diag, int w_rows, int coutp, const float* bias,
                               int kh, int kw, int stride, int pad, int blockdiag, int planes,
                               const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                               void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
@@ -617,6 +647,8 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         const bool want = !(e && atoi(e) == 0);
         { const char* b = getenv("HEAL_TC_BO"); p.bo_mode = b ? atoi(b) : 0; }
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
+        const char* ws = getenv("HEAL_TC_WSTAT");
+        p.wstat = (p.halo && blockdiag && w_diag && !(ws && atoi(ws) == 0) && p.n_tiles <= HEAL_NUM_SMS) ? 1 : 0;
     }
     CUtensorMap tmA, tmB;
     {
@@ -639,7 +671,15 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, (cuuint32_t)planes};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r;
-        if (p.halo) {
+        if (p.wstat) {
+            // packed diagonal sub-blocks {16 K, coutp, 9 taps, plane}: the whole n-tile (64 rows x 9 taps) in one box, 32B swizzle
+            cuuint64_t d4[4] = {16, (cuuint64_t)coutp, (cuuint64_t)taps, (cuuint64_t)planes};
+            cuuint64_t s4[3] = {32, (cuuint64_t)coutp * 32, (cuuint64_t)taps * coutp * 32};
+            cuuint32_t b4[4] = {16u, 64u, 9u, (cuuint32_t)planes};
+            cuuint32_t e4[4] = {1, 1, 1, 1};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_diag, d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else if (p.halo) {
             // {K, coutp, taps, plane}: one box brings the 3 horizontal taps of a kernel row
             cuuint64_t d4[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)taps, (cuuint64_t)planes};
             cuuint64_t s4[3] = {wk * 2, (cuuint64_t)coutp * wk * 2, (cuuint64_t)w_rows * wk * 2};
@@ -680,6 +720,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, p, st);
         case 64:
+            if (p.wstat && p.tma_out) return launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st);
             if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, p, st);
             return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, p, st);
         default:

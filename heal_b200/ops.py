@@ -354,10 +354,13 @@ class PackedConvTC:
         self.kh, self.kw, self.pad, self.cin, self.cout, self.coutp = kh, kw, pad, cin, cout, coutp
         self.relu, self.up, self.planes = relu, up, planes
         self.stride, self.groups, self.blockdiag = stride, groups, blockdiag
+        self.w_diag = None       # grouped convs: [plane][tap][co][16] diagonal sub-blocks (weight-stationary halo path)
 
     def to(self, device):
         self.w = self.w.to(device)
         self.bias = self.bias.to(device)
+        if self.w_diag is not None:
+            self.w_diag = self.w_diag.to(device)
         return self
 
 
@@ -407,8 +410,15 @@ def pack_conv_tc(conv, bn, relu: bool, planes: int = 2, extra_pad: int = 0) -> P
         for ci in range(cg):
             rows[:, co, col0 + ci] = wt[:, :, ci]
         wp = split_bf16(rows.reshape(kh * kw * width, 64).float(), planes)
-        return PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, width, width, width, relu, 1,
-                            planes, stride=conv.stride[0], blockdiag=True, groups=g)
+        pc = PackedConvTC(wp, b.float().contiguous(), kh, kw, conv.padding[0] + extra_pad, width, width, width, relu, 1,
+                          planes, stride=conv.stride[0], blockdiag=True, groups=g)
+        # diagonal 16x16 sub-blocks only: column = input channel inside co's 16-channel sub-block
+        diag = torch.zeros((kh * kw, width, 16), dtype=torch.float64)
+        c16 = (co // cg) * cg - (co // 16) * 16
+        for ci in range(cg):
+            diag[:, co, c16 + ci] = wt[:, :, ci]
+        pc.w_diag = split_bf16(diag.reshape(kh * kw * width, 16).float(), planes)
+        return pc
     coutp = _coutp(cout)
     rows = torch.zeros((kh * kw, coutp, cin), dtype=torch.float64)
     rows[:, :cout, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
@@ -477,7 +487,7 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
     flops = 2.0 * N * Ho * Wo * pc.cout * (pc.cin // pc.groups) * pc.kh * pc.kw * up * up
     with _Prof(fam, flops):
         rc = lib.heal_conv2d_tc(_p(x.t), x.plane_stride, N, H, W, pc.cin, x.cstride, in_coffset,
-                                _p(pc.w), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.stride, pc.pad,
+                                _p(pc.w), _p(pc.w_diag), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.stride, pc.pad,
                                 1 if pc.blockdiag else 0, pc.planes,
                                 _p(res_split), res_plane, _p(res_f32), res_cs, 0,
                                 _p(out.t) if out is not None else _vp(0), out.plane_stride if out is not None else 0,

@@ -110,9 +110,11 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
  *   stride     1 or 2 (TMA element strides on W/H)
  *   blockdiag  1: grouped 3x3 conv (Cin == Cout == coutp, channels-per-group | 64) evaluated as block-diagonal
  *              64x64 channel blocks; w_packed is then [planes][kh*kw*coutp][64] (row = tap*coutp + co,
- *              column = input channel within co's 64-channel block, zeros outside co's group) */
+ *              column = input channel within co's 64-channel block, zeros outside co's group);
+ *              w_diag (optional, NULL otherwise): the same weights as [planes][kh*kw][coutp][16] — only the 16x16 diagonal
+ *              sub-block of each output channel — kept resident in shared memory when the conv runs with one-row tiles */
 int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
-                   const void* w_packed, int w_rows, int coutp, const float* bias,
+                   const void* w_packed, const void* w_diag, int w_rows, int coutp, const float* bias,
                    int kh, int kw, int stride, int pad, int blockdiag, int planes,
                    const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                    void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
