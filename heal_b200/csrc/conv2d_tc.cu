@@ -648,7 +648,9 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         { const char* b = getenv("HEAL_TC_BO"); p.bo_mode = b ? atoi(b) : 0; }
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
         const char* ws = getenv("HEAL_TC_WSTAT");
-        p.wstat = (p.halo && blockdiag && w_diag && !(ws && atoi(ws) == 0) && p.n_tiles <= HEAL_NUM_SMS) ? 1 : 0;
+        // Off by default: measured 143 us vs 129 us for the level-0 grouped conv (profiles/): with halo loads the kernel is bound by
+        // the shared-memory reads of the A operand (each of the 3 split MMAs re-reads the 128x16 slice), not by the weight traffic.
+        p.wstat = (p.halo && blockdiag && w_diag && (ws && atoi(ws) == 1) && p.n_tiles <= HEAL_NUM_SMS) ? 1 : 0;
     }
     CUtensorMap tmA, tmB;
     {
