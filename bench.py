@@ -382,18 +382,36 @@ def main():
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms_per_frame"]) if prof else (None, None)
+        # Dominant kernel = the tcgen05 implicit-GEMM conv `k_conv2d_tc<BLOCK_N,STAGES,STG>` (one __global__ template behind every
+        # conv_tc* family below); in --precision fp32 it is the CUDA-core conv `k_conv2d_dense`.
         roofline = None
-        if dom[0] is not None:
-            ach = dom[1]["tflops"]
-            mma_per_flop = 3 if (opt.precision == "tc32" and dom[0].startswith("conv_tc")) else 1
-            roofline = {"bound": "tensor", "kernel": dom[0], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": ach / peak_tf if ach else None, "traffic": None, "peak_source": peak_src,
-                        "note": "achieved = ALGORITHMIC conv FLOPs / CUDA-event time of that kernel family; in tc32 mode every "
-                                "algorithmic FLOP issues 3 bf16 tensor-core FLOPs (tensor_pipe_tflops = 3 x achieved)",
+        if prof:
+            fam = [k for k in prof if k.startswith("conv_tc")] or [k for k in prof if k.startswith("conv_")]
+            ms = sum(prof[k]["ms_per_frame"] for k in fam)
+            gf = sum(prof[k]["gflop_per_frame"] for k in fam)
+            nl = sum(prof[k]["launches_per_frame"] for k in fam)
+            ach = (gf / 1e3) / (ms / 1e3) if ms > 0 else None
+            tc = bool(fam) and fam[0].startswith("conv_tc")
+            mma_per_flop = 3 if (opt.precision == "tc32" and tc) else 1
+            traffic = None
+            try:   # DRAM bytes per launch of the same kernel from the committed ncu pass (profiles/ncu_traffic_r1.json)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+                traffic = tj.get("k_conv2d_tc_bytes_per_launch") if tc else None
+            except Exception:
+                pass
+            roofline = {"bound": "tensor", "kernel": "k_conv2d_tc (tcgen05 implicit-GEMM conv: 1x1/3x3/grouped/strided/transposed)" if tc
+                        else "k_conv2d_dense/grouped (fp32 CUDA cores)",
+                        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if ach else None,
+                        "traffic": traffic, "peak_source": peak_src,
+                        "launches_per_frame": nl, "avg_launch_us": 1e3 * ms / nl if nl else None,
+                        "algorithmic_gflop_per_launch": gf / nl if nl else None,
+                        "note": "achieved = ALGORITHMIC conv FLOPs per launch / average CUDA-event launch duration over all launches of the "
+                                "kernel in a frame (eager instrumented pass); in tc32 mode every algorithmic FLOP issues 3 bf16 tensor-core "
+                                "FLOPs, so the tensor pipe runs at tensor_pipe_tflops = 3 x achieved; the 1x1 and grouped launches are "
+                                "HBM/L2-bound (see all_kernels), the 3x3 launches MMA-bound",
                         "tensor_pipe_tflops": ach * mma_per_flop if ach else None,
                         "tensor_pipe_frac": ach * mma_per_flop / peak_tf if ach else None,
-                        "ms_per_frame": dom[1]["ms_per_frame"], "share_of_step": dom[1]["ms_per_frame"] / (total_ms / opt.steps),
+                        "ms_per_frame": ms, "share_of_step": ms / (total_ms / opt.steps),
                         "all_kernels": prof}
         cpu = None
         if not opt.no_cpu_baseline:
