@@ -247,7 +247,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
-        os.environ["NCCL_DEBUG"] = os.environ.get("HEAL_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
+        # NCCL prints its version banner to stdout: send its log to a file so that stdout carries the single JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("HEAL_NCCL_DEBUG", "WARN")
+        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("HEAL_NCCL_DEBUG_FILE", "/tmp/heal_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from heal_b200._lib import lib
     from heal_b200 import ops, engine
@@ -269,8 +271,8 @@ def main():
         hp = torch.from_numpy(sc["points"]).pin_memory()
         ho = torch.from_numpy(sc["offsets"]).pin_memory()
         pw = torch.from_numpy(sc["pairwise"]).pin_memory()
-        host_scenes.append((hp, ho, pw))
-        dev_scenes.append((hp.to(dev), ho.to(dev), pw.to(dev)))
+        host_scenes.append((hp, ho, pw, sc["offsets"].tolist()))
+        dev_scenes.append((hp.to(dev), ho.to(dev), pw.to(dev), sc["offsets"].tolist()))
 
     use_graph = (not opt.no_graph) and not (opt.parallelism == "agent" and world > 1)
     fg = None
@@ -279,8 +281,8 @@ def main():
         cap = (max(sc["points"].shape[0] for sc in scenes) + 4095) // 4096 * 4096
         fg = FrameGraph(model, n_agents, cap, scenes[0]["pairwise"].shape)
 
-    def frame_eager(p, o, pw):
-        data = {"inputs_m1": {"points": p, "agent_offsets": o}, "agent_modality_list": ["m1"] * n_agents,
+    def frame_eager(p, o, pw, offs_host=None):
+        data = {"inputs_m1": {"points": p, "agent_offsets": o, "agent_offsets_host": offs_host}, "agent_modality_list": ["m1"] * n_agents,
                 "record_len": [n_agents], "pairwise_t_matrix": pw}
         if opt.parallelism == "agent" and world > 1:
             from heal_b200.parallel import forward_agent_sharded
@@ -288,21 +290,21 @@ def main():
         return model(data)
 
     def frame_dev(i, eager=False):
-        p, o, pw = dev_scenes[i % len(dev_scenes)]
+        p, o, pw, oh = dev_scenes[i % len(dev_scenes)]
         if fg is not None and not eager:
             fg.load(p, o, pw)          # device-to-device copy of the scene into the graph's static input buffers (timed)
             return fg.replay()
-        return frame_eager(p, o, pw)
+        return frame_eager(p, o, pw, oh)
 
     out_host = {}
 
     def frame_e2e(i):
-        hp, ho, pw = host_scenes[i % len(host_scenes)]
+        hp, ho, pw, oh = host_scenes[i % len(host_scenes)]
         if fg is not None:
             fg.load(hp, ho, pw)        # pinned host -> device, straight into the graph's input buffers
             out = fg.replay()
         else:
-            out = frame_eager(hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), pw.to(dev, non_blocking=True))
+            out = frame_eager(hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), pw.to(dev, non_blocking=True), oh)
         nbytes = 0
         for k in ("cls_preds", "reg_preds", "dir_preds"):
             if k not in out_host:
@@ -349,7 +351,8 @@ def main():
 
         # ---- instrumented pass: per-kernel-family device time (events around every C-ABI conv call) ----
         prof = None
-        if rank == 0:
+        collective_path = opt.parallelism == "agent" and world > 1      # every rank must take part in the all-gathers
+        if rank == 0 or collective_path:
             for k in range(2):                     # un-instrumented eager warm-up (allocator pools differ from the graph's)
                 frame_dev(k, eager=True)
             torch.cuda.synchronize()
