@@ -24,6 +24,7 @@ from . import ops
 from .ops import Act
 
 PRECISION = "tc32"
+SPARSE_STEM = True     # PointPillars: feed the first stride-2 residual block from the pillar list (no dense canvas)
 
 
 def set_precision(mode: str):
@@ -78,6 +79,8 @@ def conv_bn_act(x: Act, conv, bn=None, relu=False, residual: Optional[Act] = Non
     """conv(+bn)(+residual)(+relu) as ONE kernel.  `out_fmt` defaults to the mode's activation format;
     pass 'f32' for tensors that leave the conv engine (occupancy logits, prediction heads)."""
     fmt = act_fmt()
+    if isinstance(x, ops.SparseCanvas):
+        x = x.dense(fmt)
     if out is not None:
         out_fmt = out.fmt
     elif out_fmt is None:

@@ -28,12 +28,15 @@ class PointPillar(nn.Module):
 
     def forward(self, data_dict, modality_name):
         """reference signature: returns the (n, C, ny, nx) BEV map (logical NCHW, physically channels-last fp32)."""
-        return ops.act_to_nchw(self.forward_act(data_dict, modality_name, fmt="f32"))
+        return ops.act_to_nchw(self.forward_act(data_dict, modality_name, fmt="f32", sparse=False))
 
-    def forward_act(self, data_dict, modality_name, fmt=None):
-        """internal path: the canvas as an `Act` in the conv engine's activation format (no conversion pass)."""
+    def forward_act(self, data_dict, modality_name, fmt=None, sparse=None):
+        """internal path: the canvas as an `Act` in the conv engine's activation format (no conversion pass), or - when the
+        sparse stem is on - as an `ops.SparseCanvas` (pillar features + id map) that the first residual block consumes."""
+        from .. import engine
         from ..engine import act_fmt
         fmt = fmt or act_fmt()
+        sparse = engine.SPARSE_STEM if sparse is None else sparse
         require_eval(self)
         inp = data_dict[f'inputs_{modality_name}']
         nvox_dev = None
@@ -49,6 +52,9 @@ class PointPillar(nn.Module):
                                                 self.voxelize_args['max_voxels'])
             batch_size = offs.numel() - 1
         w, b = self.pillar_vfe.folded()
+        if sparse:
+            return ops.pillar_vfe_sparse(vf, vn, vc, w, b, self.voxel_size, self.lidar_range, nx=self.scatter.nx,
+                                         ny=self.scatter.ny, batch_size=batch_size, num_voxels_dev=nvox_dev)
         _, canvas = ops.pillar_vfe_scatter(vf, vn, vc, w, b, self.voxel_size, self.lidar_range,
                                            nx=self.scatter.nx, ny=self.scatter.ny, batch_size=batch_size,
                                            num_voxels_dev=nvox_dev, canvas_fmt=fmt)

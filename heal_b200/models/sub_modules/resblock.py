@@ -35,7 +35,21 @@ class BasicBlock(nn.Module):
 
     out_channels = property(lambda self: self.conv2.out_channels)
 
+    def _stem_eligible(self):
+        d = self.downsample
+        return (d is not None and self.conv1.in_channels == 64 and self.conv1.out_channels == 64 and self.conv1.stride == (2, 2)
+                and self.conv1.padding == (1, 1) and d[0].kernel_size == (1, 1) and d[0].stride == (2, 2) and d[0].out_channels == 64)
+
     def forward_nhwc(self, x, out=None):
+        if isinstance(x, ops.SparseCanvas):
+            from ... import engine
+            if engine.SPARSE_STEM and self._stem_eligible() and x.H % 2 == 0 and x.W % 2 == 0:
+                # scatter + conv1/bn1/ReLU + downsample/bn in one kernel, straight from the pillar list
+                y, idt = ops.sparse_stem(x, engine.packed(self.conv1, self.bn1, True, kind="simt"),
+                                         engine.packed(self.downsample[0], self.downsample[1], False, kind="simt"), engine.act_fmt())
+                return conv_bn_act(y, self.conv2, self.bn2, relu=True, residual=idt, out=out)
+            from ...engine import act_fmt
+            x = x.dense(act_fmt())
         idt = x
         if self.downsample is not None:
             idt = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
@@ -112,7 +126,7 @@ class ResNetModified(nn.Module):
         Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
         widest = max(max(getattr(b, "conv1").out_channels, b.out_channels) for b in blocks)
         biggest = x.N * max(x.H * x.W * max(x.C, blocks[0].conv1.out_channels), Ho * Wo * widest) * 4
-        if x.N == 1 or biggest <= self.AGENT_MAJOR_BYTES:
+        if x.N == 1 or biggest <= self.AGENT_MAJOR_BYTES or isinstance(x, ops.SparseCanvas):
             for blk in blocks:
                 x = blk.forward_nhwc(x)
             return x

@@ -669,3 +669,57 @@ def sparse_to_bev(st: SparseTensor) -> Act:
         rc = lib.heal_sparse_to_bev(_p(st.feats), _p(st.coords), _p(st.rows_dev), st.capacity, C, D, H, W, _p(out), _stream())
     check(rc, "heal_sparse_to_bev")
     return Act(out, "f32")
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse stem (PointPillars canvas never materialised)
+# ------------------------------------------------------------------------------------------------
+class SparseCanvas:
+    """Stands for the (B, ny, nx, 64) scatter canvas: pillar features + a cell -> pillar-row map.  `dense(fmt)` materialises
+    the canvas for consumers that need it; the first stride-2 residual block consumes it directly (heal_sparse_stem)."""
+
+    def __init__(self, feats, idmap, B, ny, nx, densify):
+        self.feats, self.idmap = feats, idmap
+        self.N, self.H, self.W, self.C = B, ny, nx, feats.shape[1]
+        self._densify = densify
+        self.fmt = "sparse"
+
+    @property
+    def device(self):
+        return self.feats.device
+
+    def dense(self, fmt: str = "f32") -> Act:
+        return self._densify(fmt)
+
+
+def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded, voxel_size, lidar_range,
+                      nx: int, ny: int, batch_size: int, num_voxels_dev: Optional[torch.Tensor] = None) -> SparseCanvas:
+    """PillarVFE -> pillar features (M,64) + id map; no dense canvas."""
+    pf, _ = pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded, voxel_size, lidar_range,
+                               nx, ny, batch_size, want_pillar_features=True, want_canvas=False, num_voxels_dev=num_voxels_dev)
+    coords = voxel_coords.to(torch.int32).contiguous()
+    idmap = torch.empty((batch_size, ny, nx), dtype=torch.int32, device=pf.device)
+    with _Prof("pillar_idmap"):
+        rc = lib.heal_pillar_idmap(_p(coords), _p(num_voxels_dev), coords.shape[0], batch_size, ny, nx, _p(idmap), _stream())
+    check(rc, "heal_pillar_idmap")
+
+    def densify(fmt):
+        _, canvas = pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded, voxel_size,
+                                       lidar_range, nx, ny, batch_size, num_voxels_dev=num_voxels_dev, canvas_fmt=fmt)
+        return canvas
+
+    return SparseCanvas(pf, idmap, batch_size, ny, nx, densify)
+
+
+def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_fmt: str):
+    """BasicBlock.conv1(3x3 s2 p1)+bn1+ReLU and downsample(1x1 s2)+bn from the pillar list. Returns (Act conv, Act down)."""
+    assert pc_conv.kh == 3 and pc_conv.stride == 2 and pc_conv.pad == 1 and pc_conv.cin == 64 and pc_conv.cout == 64 and pc_conv.relu
+    assert pc_down.kh == 1 and pc_down.stride == 2 and pc_down.pad == 0 and pc_down.cin == 64 and pc_down.cout == 64 and not pc_down.relu
+    o1 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
+    o2 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
+    v1, v2 = o1.view(), o2.view()
+    with _Prof("sparse_stem", 0):
+        rc = lib.heal_sparse_stem(_p(sc.feats), _p(sc.idmap), sc.N, sc.H, sc.W, _p(pc_conv.weight), _p(pc_conv.bias),
+                                  _p(pc_down.weight), _p(pc_down.bias), 64, ctypes.byref(v1), ctypes.byref(v2), _stream())
+    check(rc, "heal_sparse_stem")
+    return o1, o2

@@ -82,6 +82,18 @@ int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_po
                             const float* voxel_size3_host, const float* offset3_host, int nx, int ny,
                             float* pillar_features_out, const heal_act_t* canvas_out, void* stream);
 
+/* ---- sparse stem: scatter + the first residual block's two stride-2 convs straight from the pillar list -------------
+ * heal_pillar_idmap: (B,ny,nx) i32 map, cell -> pillar row or -1 (replaces the dense canvas of PointPillarScatter,
+ * point_pillar_scatter.py:19-77, as the conv input).
+ * heal_sparse_stem: out_conv = ReLU(bn1(conv1 3x3 stride 2 pad 1 (canvas))), out_down = bn(downsample 1x1 stride 2 (canvas))
+ * (BasicBlock, resblock.py:48-64 with the downsample of :178-187) for 64 -> 64 channels; w_conv3x3 fp32 [9][64][64]
+ * (tap, cin, cout), w_down1x1 fp32 [64][64] (cin, cout), BN folded; outputs (B, ny/2, nx/2, 64) in any storage format. */
+int heal_pillar_idmap(const int* voxel_coords, const int* num_voxels_dev, int num_voxels, int batch, int ny, int nx,
+                      int* idmap_out, void* stream);
+int heal_sparse_stem(const float* pillar_features, const int* idmap, int batch, int ny, int nx,
+                     const float* w_conv3x3, const float* b_conv3x3, const float* w_down1x1, const float* b_down1x1,
+                     int channels, const heal_act_t* out_conv, const heal_act_t* out_down, void* stream);
+
 /* ---- 2-D convolution, fp32 CUDA-core path ---------------------------------------------------
  * replaces nn.Conv2d / nn.ConvTranspose2d(k==stride) + eval BatchNorm2d + ReLU (+ residual add) of
  * resblock.py:48-64,102-122, base_bev_backbone.py:40-86, base_bev_backbone_resnet.py:54-85,

@@ -225,3 +225,39 @@ def test_warp_att_golden(golden_dir):
     g = torch.load(os.path.join(golden_dir, "warp_att.pt"), weights_only=False)
     out = ops.att_fuse(ops.to_act(g["x"].cuda()), g["affine"][0, 0, :3].cuda())
     torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), g["att"][0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc32"])
+def test_sparse_stem_equals_dense_canvas_path(prec):
+    """scatter + first residual block straight from the pillar list == the same block on the materialised canvas."""
+    from heal_b200 import ops, synth, engine
+    from heal_b200.models.sub_modules.resblock import BasicBlock, conv1x1
+    from oracle import procedural
+    old = engine.PRECISION
+    engine.set_precision(prec)
+    try:
+        sc = synth.scene(9, n_agents=2, rings=32, azimuth=512)
+        per_agent = [voxelizer.points_to_voxel_c(p, PP_VOXEL, PP_RANGE, 32, 70000) for p in sc["points"]]
+        col = {k: torch.from_numpy(v).cuda() for k, v in voxelizer.collate(per_agent).items()}
+        shapes = {"vfe.pfn_layers.0.linear.weight": (64, 10), "vfe.pfn_layers.0.norm.weight": (64,), "vfe.pfn_layers.0.norm.bias": (64,),
+                  "vfe.pfn_layers.0.norm.running_mean": (64,), "vfe.pfn_layers.0.norm.running_var": (64,)}
+        sd = procedural.make_state_dict(shapes)
+        w, b = ops.fold_linear_bn(sd["vfe.pfn_layers.0.linear.weight"], sd["vfe.pfn_layers.0.norm.weight"], sd["vfe.pfn_layers.0.norm.bias"],
+                                  sd["vfe.pfn_layers.0.norm.running_mean"], sd["vfe.pfn_layers.0.norm.running_var"], 1e-3)
+        blk = BasicBlock(64, 64, 2, torch.nn.Sequential(conv1x1(64, 64, 2), torch.nn.BatchNorm2d(64))).eval()
+        blk.load_state_dict(procedural.make_state_dict(procedural.shapes_of(blk)), strict=True)
+        blk = blk.cuda()
+        args = (col["voxel_features"], col["voxel_num_points"], col["voxel_coords"], w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2)
+        sparse = ops.pillar_vfe_sparse(*args)
+        _, dense = ops.pillar_vfe_scatter(*args, canvas_fmt=engine.act_fmt())
+        with torch.no_grad():
+            a = ops.act_to_nchw(blk.forward_nhwc(sparse)).cpu()
+            engine.SPARSE_STEM = False
+            d = ops.act_to_nchw(blk.forward_nhwc(dense)).cpu()
+            d2 = ops.act_to_nchw(blk.forward_nhwc(sparse)).cpu()          # SparseCanvas.dense() fallback
+        assert torch.equal(d, d2)
+        tol = 1e-5 if prec == "fp32" else 2e-4
+        torch.testing.assert_close(a, d, rtol=tol, atol=tol)
+    finally:
+        engine.SPARSE_STEM = True
+        engine.set_precision(old)
