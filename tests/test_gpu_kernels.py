@@ -256,8 +256,11 @@ def test_sparse_stem_equals_dense_canvas_path(prec):
             d = ops.act_to_nchw(blk.forward_nhwc(dense)).cpu()
             d2 = ops.act_to_nchw(blk.forward_nhwc(sparse)).cpu()          # SparseCanvas.dense() fallback
         assert torch.equal(d, d2)
-        tol = 1e-5 if prec == "fp32" else 2e-4
-        torch.testing.assert_close(a, d, rtol=tol, atol=tol)
+        # fp32: same fp32 FMAs in a different order; tc32: the dense path additionally rounds the canvas and conv1's output to
+        # 16-bit-mantissa split storage, so allow 1e-4 of the tensor's magnitude (1e-3 is the parity bar)
+        scale = d.abs().max().item()
+        tol = 1e-5 if prec == "fp32" else 1e-4 * max(scale, 1.0)
+        assert (a - d).abs().max().item() < tol
     finally:
         engine.SPARSE_STEM = True
         engine.set_precision(old)
