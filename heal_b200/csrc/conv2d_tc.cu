@@ -44,6 +44,7 @@ struct TcP {
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
+    int pdl;                      // launched with programmatic stream serialization
     int wstat;                    // grouped + halo: the n-tile's 16x16 diagonal weight sub-blocks (36 KiB) stay resident in smem
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
@@ -232,6 +233,13 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
+    // kernel in the stream / graph; from here on we touch memory it produced, so wait for it, and let the next kernel start
+    // its own prologue as soon as our CTAs begin to drain.
+    if (p.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int kcn = p.blockdiag ? 1 : p.kc_blocks;      // channel blocks per tap visited by one tile
@@ -598,6 +606,17 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
     if (p.wstat) grid = (grid / p.n_tiles) * p.n_tiles;       // every CTA keeps one n-tile (its weights stay in shared memory)
     if (grid < 1) return HEAL_ERR_UNSUPPORTED;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv2d_tc<BLOCK_N, STAGES, STG>, tmA, tmB, tmO, p);
+        heal_launch_counter_add(1);
+        return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
+    }
     k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, p);
     return heal_check_launch();
 }
@@ -637,6 +656,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     if (upsample > 1) p.n_tiles = w_rows / block_n;
     p.planes = planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
     { const char* e = getenv("HEAL_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("HEAL_TC_PDL"); p.pdl = e ? atoi(e) : 0; }
     p.res_split = (const __nv_bfloat16*)res_split; p.res_plane = res_plane_stride; p.res_f32 = res_f32;
     p.res_cs = res_cstride; p.res_co = res_coffset;
     p.out_split = (__nv_bfloat16*)out_split; p.out_plane = out_plane_stride; p.out_cs = out_cstride; p.out_co = out_coffset;
