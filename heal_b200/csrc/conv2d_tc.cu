@@ -17,9 +17,15 @@
 // by the TMA unit, which implements the convolution padding.  B tiles come from the packed weights
 // {Cin, taps*CoutPad, plane}.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..5 = epilogue
-// (TMEM -> registers -> bias/residual/ReLU -> split-bf16 and/or fp32 channels-last stores).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (both loop as converged warps and issue
+// under elect.sync so the tcgen05 / TMA instructions stay on the uniform datapath), warps 2..9 = epilogue, two warps per
+// TMEM lane quarter (TMEM -> registers -> bias / residual / ReLU -> hi/lo split -> swizzled smem staging -> one
+// cp.async.bulk.tensor store per 64-channel chunk; fp32 / transposed-conv outputs use direct stores).
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+// Modes: stride 2 through TMA element strides; grouped 3x3 as 16-channel sub-block MMAs on block-diagonal 64-channel
+// tiles; "halo" (3x3, stride 1, one-row tiles, N = 64): one activation box of TW+2 pixels per kernel ROW, the three
+// horizontal taps are row-shifted descriptors of the same smem tile (3x less L2->smem activation traffic).
+// HEAL_TC_* environment switches are measurement hooks (profiles/tc_experiment.py), not product paths.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
