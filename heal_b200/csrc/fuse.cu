@@ -58,8 +58,9 @@ struct FuseP {
     int n, H, W, C, align;
 };
 
-constexpr int FUSE_PIX = 32;
-
+// FUSE_PIX pixels per 256-thread block, chosen by the host so that FUSE_PIX * C / 4 == 256 (one 4-channel chunk per thread)
+// and small maps still fill the machine (64x64x256 -> 1024 blocks).
+template <int FUSE_PIX>
 __global__ void __launch_bounds__(256)
 k_pyramid_fuse(FuseP p) {
     __shared__ Tap sTap[FUSE_PIX][MAX_AGENTS];
@@ -117,15 +118,22 @@ k_pyramid_fuse(FuseP p) {
         if (pix >= HW) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < p.n; ++j) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);   // warped feature (bilinear), then weighted
+            // warped feature (bilinear), then weighted; the four tap loads are issued together, then the FMAs in tap order
+            float4 v[4];
+            float w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int off = sTap[lp][j].off[k];
-                if (off >= 0) {
-                    float w = sTap[lp][j].w[k];
-                    float4 v = act_load4(p.feat, (size_t)j * HW + off, ch * 4);
-                    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
-                }
+                w[k] = sTap[lp][j].w[k];
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (off >= 0) v[k] = act_load4(p.feat, (size_t)j * HW + off, ch * 4);
+                else w[k] = 0.f;
+            }
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a.x = fmaf(v[k].x, w[k], a.x); a.y = fmaf(v[k].y, w[k], a.y);
+                a.z = fmaf(v[k].z, w[k], a.z); a.w = fmaf(v[k].w, w[k], a.w);
             }
             acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
         }
@@ -220,8 +228,12 @@ extern "C" int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ,
     FuseP p;
     p.feat = to_view(feat); p.occ = occ; p.theta = theta; p.crop = crop_windows; p.out = to_view(out);
     p.n = n_agents; p.H = H; p.W = W; p.C = C; p.align = align_corners;
-    int grid = (H * W + FUSE_PIX - 1) / FUSE_PIX;
-    k_pyramid_fuse<<<grid, 256, 0, (cudaStream_t)stream_>>>(p);
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int HW = H * W;
+    if (C >= 256)      k_pyramid_fuse<4><<<(HW + 3) / 4, 256, 0, st>>>(p);
+    else if (C >= 128) k_pyramid_fuse<8><<<(HW + 7) / 8, 256, 0, st>>>(p);
+    else if (C >= 64)  k_pyramid_fuse<16><<<(HW + 15) / 16, 256, 0, st>>>(p);
+    else               k_pyramid_fuse<32><<<(HW + 31) / 32, 256, 0, st>>>(p);
     return heal_check_launch();
 }
 

@@ -61,7 +61,11 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     for (int k = 0; k < PV_CIN; ++k) { w0[k] = sW[k * PV_COUT + 2 * lane]; w1[k] = sW[k * PV_COUT + 2 * lane + 1]; }
     float b0 = sB[2 * lane], b1 = sB[2 * lane + 1];
     float m0 = 0.f, m1 = 0.f;  // ReLU output >= 0, so 0 is the identity of the running max
-    for (int t = 0; t < c.T; ++t) {
+    // padded slots are all-zero rows: Linear gives +0, so each contributes exactly ReLU(b) to the max -- fold them into one
+    // fmaxf instead of T - n dead dot products (LiDAR pillars hold ~3 points of T = 32)
+    const int nt = min(n, c.T);
+    if (nt < c.T) { m0 = fmaxf(m0, b0); m1 = fmaxf(m1, b1); }
+    for (int t = 0; t < nt; ++t) {
         const float4* ft = reinterpret_cast<const float4*>(sF[warp][t]);
         float4 a = ft[0], b = ft[1], d = ft[2];
         float x[PV_CIN] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y};

@@ -259,8 +259,9 @@ def test_sparse_stem_equals_dense_canvas_path(prec):
         # fp32: same fp32 FMAs in a different order; tc32: the dense path additionally rounds the canvas and conv1's output to
         # 16-bit-mantissa split storage, so allow 1e-4 of the tensor's magnitude (1e-3 is the parity bar)
         scale = d.abs().max().item()
-        tol = 1e-5 if prec == "fp32" else 1e-4 * max(scale, 1.0)
-        assert (a - d).abs().max().item() < tol
+        tol = (1e-5 if prec == "fp32" else 1e-4) * max(scale, 1.0)
+        err = (a - d).abs().max().item()
+        assert err < tol, (err, tol, scale)
     finally:
         engine.SPARSE_STEM = True
         engine.set_precision(old)
