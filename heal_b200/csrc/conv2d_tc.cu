@@ -55,7 +55,7 @@ struct TcP {
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
-    int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads
+    int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads, 8 no residual loads (TMA-store epilogue), 16 no MMAs
     const float* bias;            // [Cout]
     // residual (optional): split planes or fp32
     const __nv_bfloat16* res_split; size_t res_plane; const float* res_f32; int res_cs, res_co;
@@ -315,6 +315,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (p.halo) {
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
                         if (elect_one()) {
+                            if (!(p.dbg & 16))
 #pragma unroll
                             for (int s = 0; s < 3; ++s) {
                                 // tap s reads rows [s, s+128) of the halo tile: start address + s*128 B, swizzle phase in base_offset
@@ -362,6 +363,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
                     const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES), b_lo = umma_desc_sw128(sb + B_TILE_BYTES);
                     if (elect_one()) {
+                    if (!(p.dbg & 16))
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per 16-element K step
@@ -408,6 +410,31 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr int CHUNK = (BLOCK_N >= 32) ? 32 : 16;
         int acc = 0; uint32_t acc_phase = 0;
         int stg_count = 0;
+        // Residual prefetch (TMA-store epilogue, split/bf16 residual): the 2 x 4 x 16 B of this thread's row for the NEXT 64-channel
+        // chunk are requested one chunk ahead, so their DRAM latency hides behind the current chunk (and the wait for the MMAs)
+        // instead of stalling every 8-channel group (measured: level-0 conv3 105 -> 44 us with the loads removed).
+        uint4 rn_h[4], rn_l[4];
+        const bool res_pf = (STG > 0 && BLOCK_N >= 64) && p.tma_out && p.res_split && !(p.dbg & 8);
+        auto res_fetch = [&](int tile_, int c64_) {
+            const int nt_ = tile_ % p.n_tiles, mt_ = tile_ / p.n_tiles;
+            const int tw_ = mt_ % p.tiles_w; const int t2_ = mt_ / p.tiles_w;
+            const int th_ = t2_ % p.tiles_h; const int img_ = t2_ / p.tiles_h;
+            const int oh_ = th_ * p.TH + row / p.TW, ow_ = tw_ * p.TW + row % p.TW;
+            const int ng_ = nt_ * BLOCK_N;
+            const int q_ = ng_ / p.coutp, c0_ = ng_ % p.coutp + c64_ * 64 + chalf * 32;
+            const size_t pix_ = ((size_t)img_ * (p.Ho * p.up) + (size_t)(oh_ * p.up + q_ / p.up)) * (size_t)(p.Wo * p.up) + (size_t)(ow_ * p.up + q_ % p.up);
+            const bool ok_ = (oh_ < p.Ho) && (ow_ < p.Wo);
+            const __nv_bfloat16* rp = p.res_split + pix_ * p.res_cs + p.res_co + c0_;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                rn_h[g] = make_uint4(0u, 0u, 0u, 0u); rn_l[g] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok_ && c0_ + g * 8 + 8 <= p.Cout) {
+                    rn_h[g] = __ldg(reinterpret_cast<const uint4*>(rp + g * 8));
+                    if (p.planes == 2) rn_l[g] = __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane + g * 8));
+                }
+            }
+        };
+        if (res_pf && (int)blockIdx.x < total_tiles) res_fetch(blockIdx.x, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
@@ -426,6 +453,13 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
                 for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
                     const int b = stg_count % STG;
+                    uint4 rc_h[4], rc_l[4];
+                    if (res_pf) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) { rc_h[g] = rn_h[g]; rc_l[g] = rn_l[g]; }
+                        if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
+                        else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
+                    }
                     // (A) buffer b is free once at most STG-1 store groups are still reading shared memory
                     if (warp == 2 && lane == 0) bulk_wait_read<STG - 1>();
                     epi_bar(1);
@@ -441,20 +475,17 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
-                        if (valid && c + 8 <= p.Cout) {
-                            if (p.res_split) {
-                                const __nv_bfloat16* rp = p.res_split + pix * p.res_cs + p.res_co + c;
-                                uint4 h = __ldg(reinterpret_cast<const uint4*>(rp));
-                                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+                        if (res_pf) {
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rc_h[g8]);
+                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rc_l[g8]);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
-                                if (p.planes == 2) {
-                                    uint4 l = __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane));
-                                    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+                            for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
+                            if (p.planes == 2) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
-                                }
-                            } else if (p.res_f32) {
+                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
+                            }
+                        } else if (valid && c + 8 <= p.Cout && !(p.dbg & 8)) {
+                            if (p.res_f32) {
                                 const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
