@@ -55,6 +55,7 @@ struct TcP {
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
+    int res_tma;                  // STG == 3: the residual chunk is TMA-loaded into the staging buffer one chunk ahead (tmR valid)
     int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads, 8 no residual loads (TMA-store epilogue), 16 no MMAs
     const float* bias;            // [Cout]
     // residual (optional): split planes or fp32
@@ -200,7 +201,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BLOCK_N, int STAGES, int STG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmO, const TcP p) {
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcP p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024 B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -215,8 +216,9 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* wreg = smem + (size_t)STAGES * stage_bytes;                  // 1024-aligned (stage_bytes is a multiple of 1024)
     uint8_t* stg = wreg + w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], weights_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], weights_full, residual_full[3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    const uint32_t bar_res = smem_u32(bars + 2 * STAGES + 5);
     const uint32_t bar_w = smem_u32(bars + 2 * STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
@@ -229,6 +231,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 256); }
         mbar_init(bar_w, 1);
+        for (int a = 0; a < 3; ++a) mbar_init(bar_res + 8 * a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -414,7 +417,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // chunk are requested one chunk ahead, so their DRAM latency hides behind the current chunk (and the wait for the MMAs)
         // instead of stalling every 8-channel group (measured: level-0 conv3 105 -> 44 us with the loads removed).
         uint4 rn_h[4], rn_l[4];
-        const bool res_pf = (STG > 0 && BLOCK_N >= 64) && p.tma_out && p.res_split && !(p.dbg & 8);
+        const bool res_tma = (STG == 3) && p.res_tma && !(p.dbg & 8);
+        const bool res_pf = (STG > 0 && BLOCK_N >= 64) && p.tma_out && p.res_split && !res_tma && !(p.dbg & 8);
         auto res_fetch = [&](int tile_, int c64_) {
             const int nt_ = tile_ % p.n_tiles, mt_ = tile_ / p.n_tiles;
             const int tw_ = mt_ % p.tiles_w; const int t2_ = mt_ / p.tiles_w;
@@ -435,6 +439,16 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         };
         if (res_pf && (int)blockIdx.x < total_tiles) res_fetch(blockIdx.x, 0);
+        // TMA variant (STG == 3): residual chunk i+1 lands in staging buffer (i+1) % 3 while chunk i is processed; the epilogue
+        // then adds it IN PLACE (same swizzled 16 B slots it will overwrite with the output) -- fully coalesced, no registers.
+        auto res_tma_issue = [&](int tile_, int c64_, int buf_) {
+            const int nt_ = tile_ % p.n_tiles, mt_ = tile_ / p.n_tiles;
+            const int tw_ = mt_ % p.tiles_w; const int t2_ = mt_ / p.tiles_w;
+            const int th_ = t2_ % p.tiles_h; const int img_ = t2_ / p.tiles_h;
+            mbar_expect_tx(bar_res + 8 * buf_, (uint32_t)stg_bytes);
+            tma_load_5d(smem_u32(stg) + buf_ * stg_bytes, &tmR, bar_res + 8 * buf_, (nt_ * BLOCK_N) % p.coutp + c64_ * 64, tw_ * p.TW, th_ * p.TH, img_, 0);
+        };
+        if (res_tma && warp == 2 && lane == 0 && (int)blockIdx.x < total_tiles) res_tma_issue(blockIdx.x, 0, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
@@ -460,9 +474,20 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
                         else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
                     }
-                    // (A) buffer b is free once at most STG-1 store groups are still reading shared memory
-                    if (warp == 2 && lane == 0) bulk_wait_read<STG - 1>();
-                    epi_bar(1);
+                    if (res_tma) {
+                        // (A') store(i-2) has left buffer (i+1) % 3 -> request residual(i+1) into it, then wait for residual(i) in buffer b
+                        if (warp == 2 && lane == 0) {
+                            bulk_wait_read<1>();
+                            int ntile = tile, nc = c64 + 1;
+                            if (nc == BLOCK_N / 64) { nc = 0; ntile = tile + (int)gridDim.x; }
+                            if (ntile < total_tiles) res_tma_issue(ntile, nc, (stg_count + 1) % STG);
+                        }
+                        mbar_wait(bar_res + 8 * b, (uint32_t)((stg_count / STG) & 1));
+                    } else {
+                        // (A) buffer b is free once at most STG-1 store groups are still reading shared memory
+                        if (warp == 2 && lane == 0) bulk_wait_read<STG - 1>();
+                        epi_bar(1);
+                    }
                     // (B) this warp's 32 columns of the 64-column chunk -> registers -> epilogue -> swizzled smem
                     uint32_t raw[32];
                     const int col0 = c64 * 64 + chalf * 32;
@@ -475,7 +500,21 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
-                        if (res_pf) {
+                        const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
+                        if (res_tma) {
+                            uint4 h, l = make_uint4(0u, 0u, 0u, 0u);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(srow + chunk16) : "memory");
+                            if (p.planes == 2)
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(srow + A_TILE_BYTES + chunk16) : "memory");
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
+                            if (p.planes == 2) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
+                            }
+                        } else if (res_pf) {
                             const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rc_h[g8]);
                             const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rc_l[g8]);
 #pragma unroll
@@ -501,7 +540,6 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { hw[j] = pack_bf16(v[2 * j], v[2 * j + 1]); lw[j] = pack_bf16(lo[2 * j], lo[2 * j + 1]); }
-                        const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk16), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
                         if (p.planes == 2)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + A_TILE_BYTES + chunk16), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
@@ -628,7 +666,9 @@ PFN_tmEncodeTiled get_encode() {
 }
 
 template <int BLOCK_N, int STAGES, int STG>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TcP& p, cudaStream_t st) {
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const TcP& p_in, cudaStream_t st) {
+    TcP p = p_in;
+    p.res_tma = (STG == 3 && p.tma_out && p.res_split) ? 1 : 0;
     size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2);
     if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (p.wstat ? 0 : (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2);
     size_t smem = 1024 + (size_t)STAGES * stage_bytes + (p.wstat ? (size_t)p.planes * 9 * 2048 : 0) + (size_t)STG * p.planes * A_TILE_BYTES + 256;
@@ -650,11 +690,11 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv2d_tc<BLOCK_N, STAGES, STG>, tmA, tmB, tmO, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv2d_tc<BLOCK_N, STAGES, STG>, tmA, tmB, tmO, tmR, p);
         heal_launch_counter_add(1);
         return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
     }
-    k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, p);
+    k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, tmR, p);
     return heal_check_launch();
 }
 
@@ -773,17 +813,39 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             p.tma_out = out_f32 ? 0 : 1;
         }
     }
+    // residual tensor map (same boxes as the output map): the residual chunk is TMA-loaded into the output staging buffer
+    CUtensorMap tmR = tmO;
+    bool res_tma_ok = false;
+    {
+        const char* e = getenv("HEAL_TC_RES_TMA");
+        const bool want = !(e && atoi(e) == 0);
+        if (want && p.tma_out && res_split && !p.halo) {
+            cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N, (cuuint64_t)planes};
+            cuuint64_t strides[4] = {(cuuint64_t)res_cstride * 2, (cuuint64_t)Wo * res_cstride * 2, (cuuint64_t)Ho * Wo * res_cstride * 2,
+                                     (cuuint64_t)res_plane_stride * 2};
+            if (planes == 1) strides[3] = strides[2] * N;
+            cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1u, (cuuint32_t)planes};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            void* base = (void*)((const __nv_bfloat16*)res_split + res_coffset);
+            CUresult r = enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
+            res_tma_ok = true;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream_;
     const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
     switch (block_n) {
-        case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, p, st);
-        case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, p, st);
+        case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, tmR, p, st);
+        case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 64:
-            if (p.wstat && p.tma_out) return launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st);
-            if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, p, st);
-            return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, p, st);
+            if (p.wstat && p.tma_out) return launch_tc<64, 3, 2>(tmA, tmB, tmO, tmR, p, st);
+            if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, tmR, p, st);
+            if (res_tma_ok) return launch_tc<64, 2, 3>(tmA, tmB, tmO, tmR, p, st);
+            return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         default:
-            if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, p, st);
-            return kblocks <= 4 ? launch_tc<128, 2, 2>(tmA, tmB, tmO, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, p, st);
+            if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, tmR, p, st);
+            if (res_tma_ok) return launch_tc<128, 2, 3>(tmA, tmB, tmO, tmR, p, st);
+            return kblocks <= 4 ? launch_tc<128, 2, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, tmR, p, st);
     }
 }
