@@ -51,7 +51,6 @@ struct TcP {
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
     int pdl;                      // launched with programmatic stream serialization
-    int wstat;                    // grouped + halo: the n-tile's 16x16 diagonal weight sub-blocks (36 KiB) stay resident in smem
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
@@ -116,17 +115,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-    return d;
-}
-
-// K-major, 32B-swizzled descriptor (rows of 32 B = 16 bf16, 8-row groups 256 B apart): the packed diagonal weight sub-blocks.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                           // SWIZZLE_32B
     return d;
 }
 
@@ -209,28 +197,30 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
     const int halo_a_plane = (p.TW + 2) * 128;
     const int halo_a_bytes = (p.planes * halo_a_plane + 1023) & ~1023;
-    const int stage_bytes = p.wstat ? halo_a_bytes
-                          : (p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES));
-    const int w_bytes = p.wstat ? p.planes * 9 * 2048 : 0;                // [plane][9 taps][64 rows][32 B] resident weights
+    const int stage_bytes = p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES);
     const int stg_bytes = p.planes * A_TILE_BYTES;                        // one staging buffer: [plane][128 rows][128 B]
-    uint8_t* wreg = smem + (size_t)STAGES * stage_bytes;                  // 1024-aligned (stage_bytes is a multiple of 1024)
-    uint8_t* stg = wreg + w_bytes;
+    uint8_t* stg = smem + (size_t)STAGES * stage_bytes;                   // 1024-aligned (stage_bytes is a multiple of 1024)
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], weights_full, residual_full[3]
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], (spare), residual_full[3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
     const uint32_t bar_res = smem_u32(bars + 2 * STAGES + 5);
-    const uint32_t bar_w = smem_u32(bars + 2 * STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    // Split-bf16 products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  For BLOCK_N <= 64 the hi and lo weight planes sit next to each other
+    // in shared memory, so ONE MMA with N' = 2N computes a_hi x [b_hi | b_lo] (main | aux accumulator columns) and a second
+    // N-wide MMA adds a_lo x b_hi: 2 tensor-core instructions and 2 reads of the A slice per K step instead of 3 (these tile
+    // shapes are bound by the A-operand shared-memory reads: a 128x16 N=16 MMA costs ~2/3 of an N=128 one).  The epilogue
+    // adds aux to main.  BLOCK_N = 128 keeps 3 MMAs (N' = 256 would be the same tensor time and needs all of TMEM).
+    constexpr bool NCAT = (BLOCK_N <= 64);
+    constexpr int ACC_STRIDE = NCAT ? 2 * BLOCK_N : BLOCK_N;      // TMEM columns per accumulator buffer
+    constexpr int TMEM_COLS = (2 * ACC_STRIDE < 32) ? 32 : 2 * ACC_STRIDE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 256); }
-        mbar_init(bar_w, 1);
         for (int a = 0; a < 3; ++a) mbar_init(bar_res + 8 * a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,13 +248,6 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ============================== TMA producer (whole warp loops, one elected lane issues) ==
         {
             int stage = 0; uint32_t phase = 0;
-            if (p.wstat) {          // gridDim.x is a multiple of n_tiles: this CTA keeps n-tile blockIdx.x % n_tiles for its whole life
-                if (elect_one()) {
-                    mbar_expect_tx(bar_w, (uint32_t)w_bytes);
-                    tma_load_4d(smem_u32(wreg), &tmB, bar_w, 0, (int)(blockIdx.x % p.n_tiles) * BLOCK_N, 0, 0);
-                }
-                __syncwarp();
-            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw_i = mt % p.tiles_w; const int t2 = mt / p.tiles_w;
@@ -278,9 +261,11 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // k-block = (kernel row tap, channel block): pixels [w0-1, w0+TW] of input row h0+tap-1, and the 3 taps' weights
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
                         if (elect_one()) {
-                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + (p.wstat ? 0 : 3 * B_TILE_BYTES))));
+                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + 3 * B_TILE_BYTES)));
                             tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 - 1, h0 + tap - 1, img, 0);
-                            if (!p.wstat) tma_load_4d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, nt * BLOCK_N, tap * 3, 0);
+                            // B lands as [tap][plane][rows] (dense) or [tap][16-row sub-block][plane][16 rows] (block-diagonal)
+                            if (p.blockdiag) tma_load_5d(sb, &tmB, bar_full + 8 * stage, 0, 0, 0, nt * (BLOCK_N / 16), tap * 3);
+                            else tma_load_4d(sb, &tmB, bar_full + 8 * stage, kc * BLOCK_K, nt * BLOCK_N, 0, tap * 3);
                         }
                         __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -292,7 +277,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (elect_one()) {
                         mbar_expect_tx(bar_full + 8 * stage, (uint32_t)((ldA ? p.planes * A_TILE_BYTES : 0) + (ldB ? p.planes * B_TILE_BYTES : 0)));
                         if (ldA) tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, img, 0);
-                        if (ldB) tma_load_3d(sb, &tmB, bar_full + 8 * stage, p.blockdiag ? 0 : kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);
+                        if (ldB) {
+                            if (p.blockdiag) tma_load_4d(sb, &tmB, bar_full + 8 * stage, 0, 0, 0, (tap * p.coutp + nt * BLOCK_N) / 16);   // [sub-block][plane][16 rows]
+                            else tma_load_3d(sb, &tmB, bar_full + 8 * stage, kc * BLOCK_K, tap * p.coutp + nt * BLOCK_N, 0);                // [plane][rows]
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -305,97 +293,67 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            // N-concatenated forms (NCAT): N' = 2N
+            const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            const uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            const bool split = (p.planes == 2);
+            const int sub_cols = (NCAT && split) ? 32 : 16;          // accumulator columns per 16-channel diagonal sub-block
+            const int sub_bytes = p.planes * 2048;                   // smem bytes per sub-block: [plane][16 rows][128 B]
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            if (p.wstat) { mbar_wait(bar_w, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    if (p.halo) {
-                        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
-                        if (elect_one()) {
-                            if (!(p.dbg & 16))
+                    // A: [plane][rows][128 B]; halo mode: tap s reads rows [s, s+128) of the (TW+2)-row tile (start address + s*128 B;
+                    // the swizzle is a function of the absolute smem address, so no base offset)
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t a_plane = p.halo ? (uint32_t)halo_a_plane : (uint32_t)A_TILE_BYTES;
+                    const uint32_t sb = sa + (p.halo ? (uint32_t)halo_a_bytes : (uint32_t)(p.planes * A_TILE_BYTES));
+                    const int ntap = p.halo ? 3 : 1;
+                    if (elect_one()) {
+                        if (!(p.dbg & 16))
+                        for (int s = 0; s < ntap; ++s) {
+                            const uint32_t ah = sa + s * 128, al = ah + a_plane;
+                            const uint32_t bs = sb + s * p.planes * B_TILE_BYTES;
 #pragma unroll
-                            for (int s = 0; s < 3; ++s) {
-                                // tap s reads rows [s, s+128) of the halo tile: start address + s*128 B, swizzle phase in base_offset
-                                const uint32_t ah = sa + s * 128, al = ah + halo_a_plane;
-                                const uint32_t bh = sb + s * B_TILE_BYTES, bl = bh + 3 * B_TILE_BYTES;
-#pragma unroll
-                                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                    const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32, p.bo_mode), a_lo = umma_desc_sw128_off(al + k * 32, p.bo_mode);
-                                    if (p.blockdiag) {
-                                        const uint32_t bo = k * 16 * 128 + k * 32;
-                                        // resident weights: [plane][tap][sub-block k: 16 rows x 32 B]; tap = (kernel row kb) * 3 + s
-                                        const uint32_t ws = smem_u32(wreg) + (uint32_t)((kb * 3 + s) * 2048 + k * 512);
-                                        const uint64_t b_hi = p.wstat ? umma_desc_sw32(ws) : umma_desc_sw128(bh + bo);
-                                        const uint64_t b_lo = p.wstat ? umma_desc_sw32(ws + 9 * 2048) : umma_desc_sw128(bl + bo);
-                                        const uint32_t td = tmem_d + (uint32_t)(k * 16);
-                                        const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
-                                        if (p.planes == 2) {
-                                            umma_bf16(td, a_lo, b_hi, idesc16, f0);
-                                            umma_bf16(td, a_hi, b_lo, idesc16, 1u);
-                                            umma_bf16(td, a_hi, b_hi, idesc16, 1u);
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32, p.bo_mode), a_lo = umma_desc_sw128_off(al + k * 32, p.bo_mode);
+                                if (p.blockdiag) {
+                                    // Grouped conv: channels-per-group divides 16, so output channels [16k,16k+16) of this 64-block depend
+                                    // only on input channels [16k,16k+16): one M128 x N16 x K16 product per 16-channel sub-block.
+                                    const uint32_t bk = bs + k * sub_bytes + k * 32;            // sub-block k, K offset k*16 elements
+                                    const uint32_t td = tmem_d + (uint32_t)(k * sub_cols);
+                                    const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
+                                    if constexpr (NCAT) {
+                                        if (split) {
+                                            umma_bf16(td, a_hi, umma_desc_sw128(bk), idesc32, f0);      // [a_hi*b_hi | a_hi*b_lo]
+                                            umma_bf16(td, a_lo, umma_desc_sw128(bk), idesc16, 1u);      // += a_lo*b_hi
                                         } else {
-                                            umma_bf16(td, a_hi, b_hi, idesc16, f0);
+                                            umma_bf16(td, a_hi, umma_desc_sw128(bk), idesc16, f0);
                                         }
+                                    }
+                                } else {
+                                    const uint32_t first = (kb == 0 && s == 0 && k == 0) ? 0u : 1u;
+                                    const uint64_t b_hi = umma_desc_sw128(bs + k * 32);
+                                    if (!split) {
+                                        umma_bf16(tmem_d, a_hi, b_hi, idesc, first);
+                                    } else if constexpr (NCAT) {
+                                        umma_bf16(tmem_d, a_hi, b_hi, idesc_cat, first);                // [a_hi*b_hi | a_hi*b_lo]
+                                        umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);                       // += a_lo*b_hi
                                     } else {
-                                        const uint64_t b_hi = umma_desc_sw128(bh + k * 32), b_lo = umma_desc_sw128(bl + k * 32);
-                                        const uint32_t first = (kb == 0 && s == 0 && k == 0) ? 0u : 1u;
-                                        if (p.planes == 2) {
-                                            umma_bf16(tmem_d, a_lo, b_hi, idesc, first);
-                                            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-                                            umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
-                                        } else {
-                                            umma_bf16(tmem_d, a_hi, b_hi, idesc, first);
-                                        }
+                                        const uint64_t b_lo = umma_desc_sw128(bs + B_TILE_BYTES + k * 32);
+                                        umma_bf16(tmem_d, a_lo, b_hi, idesc, first);
+                                        umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                                        umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
                                     }
                                 }
                             }
-                            umma_commit(bar_empty + 8 * stage);
                         }
-                        __syncwarp();
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
-                    const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint32_t sb = sa + p.planes * A_TILE_BYTES;
-                    const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
-                    const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES), b_lo = umma_desc_sw128(sb + B_TILE_BYTES);
-                    if (elect_one()) {
-                    if (!(p.dbg & 16))
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per 16-element K step
-                        if (p.blockdiag) {
-                            // Grouped conv: channels-per-group divides 16, so output channels [16k,16k+16) of this 64-block
-                            // depend only on input channels [16k,16k+16): one M128 x N16 x K16 MMA per 16-channel
-                            // sub-block (B rows 16k.. = +2048 B, D columns 16k..) instead of a 64x64 block.
-                            const uint64_t bo = ko + (uint64_t)((k * 16 * 128) >> 4);
-                            const uint32_t td = tmem_d + (uint32_t)(k * 16);
-                            const uint32_t f0 = (kb == 0) ? 0u : 1u;
-                            if (p.planes == 2) {
-                                umma_bf16(td, a_lo + ko, b_hi + bo, idesc16, f0);
-                                umma_bf16(td, a_hi + ko, b_lo + bo, idesc16, 1u);
-                                umma_bf16(td, a_hi + ko, b_hi + bo, idesc16, 1u);
-                            } else {
-                                umma_bf16(td, a_hi + ko, b_hi + bo, idesc16, f0);
-                            }
-                            continue;
-                        }
-                        const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-                        if (p.planes == 2) {
-                            umma_bf16(tmem_d, a_lo + ko, b_hi + ko, idesc, first);
-                            umma_bf16(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-                            umma_bf16(tmem_d, a_hi + ko, b_hi + ko, idesc, 1u);
-                        } else {
-                            umma_bf16(tmem_d, a_hi + ko, b_hi + ko, idesc, first);
-                        }
-                    }
-                    umma_commit(bar_empty + 8 * stage);       // smem slot free once these MMAs retire
+                        umma_commit(bar_empty + 8 * stage);       // smem slot free once these MMAs retire
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -416,9 +374,39 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // Residual prefetch (TMA-store epilogue, split/bf16 residual): the 2 x 4 x 16 B of this thread's row for the NEXT 64-channel
         // chunk are requested one chunk ahead, so their DRAM latency hides behind the current chunk (and the wait for the MMAs)
         // instead of stalling every 8-channel group (measured: level-0 conv3 105 -> 44 us with the loads removed).
+        // CH logical accumulator columns [col0, col0+CH) of buffer `acc` -> raw (fp32 bits); with the N-concatenated split MMAs the
+        // value is main + aux: dense = columns c and BLOCK_N + c, block-diagonal = per 16-channel sub-block [main16 | aux16].
+        auto ld_acc = [&](int col0, uint32_t* raw) {
+            const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+            if (NCAT && p.planes == 2) {
+                uint32_t y[CHUNK];
+                if constexpr (CHUNK == 32) {
+                    if (p.blockdiag) {
+                        tmem_ld32(tb + (uint32_t)(2 * col0), raw); tmem_ld32(tb + (uint32_t)(2 * col0 + 32), y);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw[16 + j]));
+                            raw[16 + j] = __float_as_uint(__uint_as_float(y[j]) + __uint_as_float(y[16 + j]));
+                        }
+                        return;
+                    }
+                    tmem_ld32(tb + (uint32_t)col0, raw); tmem_ld32(tb + (uint32_t)(BLOCK_N + col0), y);
+                } else {
+                    tmem_ld16(tb + (uint32_t)col0, raw); tmem_ld16(tb + (uint32_t)(BLOCK_N + col0), y);
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(y[j]));
+            } else {
+                if constexpr (CHUNK == 32) tmem_ld32(tb + (uint32_t)col0, raw); else tmem_ld16(tb + (uint32_t)col0, raw);
+                tmem_wait_ld();
+            }
+        };
         uint4 rn_h[4], rn_l[4];
         const bool res_tma = (STG == 3) && p.res_tma && !(p.dbg & 8);
-        const bool res_pf = (STG > 0 && BLOCK_N >= 64) && p.tma_out && p.res_split && !res_tma && !(p.dbg & 8);
+        constexpr bool RES_PF = (STG == 1 && BLOCK_N == 64);      // the halo configuration: no room for 3 staging buffers
+        const bool res_pf = RES_PF && p.tma_out && p.res_split && !(p.dbg & 8);
         auto res_fetch = [&](int tile_, int c64_) {
             const int nt_ = tile_ % p.n_tiles, mt_ = tile_ / p.n_tiles;
             const int tw_ = mt_ % p.tiles_w; const int t2_ = mt_ / p.tiles_w;
@@ -438,7 +426,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
         };
-        if (res_pf && (int)blockIdx.x < total_tiles) res_fetch(blockIdx.x, 0);
+        if (RES_PF && res_pf && (int)blockIdx.x < total_tiles) res_fetch(blockIdx.x, 0);
         // TMA variant (STG == 3): residual chunk i+1 lands in staging buffer (i+1) % 3 while chunk i is processed; the epilogue
         // then adds it IN PLACE (same swizzled 16 B slots it will overwrite with the output) -- fully coalesced, no registers.
         auto res_tma_issue = [&](int tile_, int c64_, int buf_) {
@@ -467,13 +455,6 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
                 for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
                     const int b = stg_count % STG;
-                    uint4 rc_h[4], rc_l[4];
-                    if (res_pf) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) { rc_h[g] = rn_h[g]; rc_l[g] = rn_l[g]; }
-                        if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
-                        else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
-                    }
                     if (res_tma) {
                         // (A') store(i-2) has left buffer (i+1) % 3 -> request residual(i+1) into it, then wait for residual(i) in buffer b
                         if (warp == 2 && lane == 0) {
@@ -491,15 +472,34 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // (B) this warp's 32 columns of the 64-column chunk -> registers -> epilogue -> swizzled smem
                     uint32_t raw[32];
                     const int col0 = c64 * 64 + chalf * 32;
-                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col0), raw);
-                    tmem_wait_ld();
+                    ld_acc(col0, raw);
+                    bool pre = false;
+                    if (RES_PF && res_pf) {
+                        // fold bias + residual (prefetched one chunk ago) into raw, then reuse the registers for the next chunk's request
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const int c = ch0 + col0 + g8 * 8;
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rn_h[g8]);
+                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rn_l[g8]);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float v = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
+                                v += __bfloat162float(hb[j]);
+                                if (p.planes == 2) v += __bfloat162float(lb[j]);
+                                raw[g8 * 8 + j] = __float_as_uint(v);
+                            }
+                        }
+                        pre = true;
+                        if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
+                        else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
+                    }
                     const uint32_t srow = stg_base + b * stg_bytes + row * 128;
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
                         const int c = ch0 + col0 + g8 * 8;
                         float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((!pre && p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
                         const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
                         if (res_tma) {
                             uint4 h, l = make_uint4(0u, 0u, 0u, 0u);
@@ -514,15 +514,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
                             }
-                        } else if (res_pf) {
-                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rc_h[g8]);
-                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rc_l[g8]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
-                            if (p.planes == 2) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
-                            }
+                        } else if (pre) {
+                            // bias + residual already folded into raw
                         } else if (valid && c + 8 <= p.Cout && !(p.dbg & 8)) {
                             if (p.res_f32) {
                                 const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
@@ -562,9 +555,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
             for (int cc = chalf; cc < BLOCK_N / CHUNK; cc += 2) {
                 uint32_t raw[CHUNK];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * CHUNK);
-                if (CHUNK == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
-                tmem_wait_ld();
+                ld_acc(cc * CHUNK, raw);
                 const int c_first = ch0 + cc * CHUNK;
                 if (valid && c_first < p.Cout) {
 #pragma unroll
@@ -670,8 +661,8 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     TcP p = p_in;
     p.res_tma = (STG == 3 && p.tma_out && p.res_split) ? 1 : 0;
     size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2);
-    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (p.wstat ? 0 : (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2);
-    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (p.wstat ? (size_t)p.planes * 9 * 2048 : 0) + (size_t)STG * p.planes * A_TILE_BYTES + 256;
+    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2;
+    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -681,7 +672,6 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     }
     int total = p.m_tiles * p.n_tiles;
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
-    if (p.wstat) grid = (grid / p.n_tiles) * p.n_tiles;       // every CTA keeps one n-tile (its weights stay in shared memory)
     if (grid < 1) return HEAL_ERR_UNSUPPORTED;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
@@ -744,10 +734,6 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         const bool want = !(e && atoi(e) == 0);
         { const char* b = getenv("HEAL_TC_BO"); p.bo_mode = b ? atoi(b) : 0; }
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
-        const char* ws = getenv("HEAL_TC_WSTAT");
-        // Off by default: measured 143 us vs 129 us for the level-0 grouped conv (profiles/): with halo loads the kernel is bound by
-        // the shared-memory reads of the A operand (each of the 3 split MMAs re-reads the 128x16 slice), not by the weight traffic.
-        p.wstat = (p.halo && blockdiag && w_diag && (ws && atoi(ws) == 1) && p.n_tiles <= HEAL_NUM_SMS) ? 1 : 0;
     }
     CUtensorMap tmA, tmB;
     {
@@ -764,30 +750,36 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
     }
     {
+        // packed weights in global memory: [plane][taps * coutp rows][wk] bf16.  The box order decides the shared-memory layout:
+        // hi and lo planes of the same rows must be adjacent for the N-concatenated MMAs (see NCAT in the kernel).
         const cuuint64_t wk = blockdiag ? 64 : Cin;      // K extent of the packed weight matrix
-        cuuint64_t dims[3] = {wk, (cuuint64_t)w_rows, (cuuint64_t)planes};
-        cuuint64_t strides[2] = {wk * 2, (cuuint64_t)w_rows * wk * 2};
-        cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, (cuuint32_t)planes};
-        cuuint32_t es[3] = {1, 1, 1};
+        const cuuint64_t row_b = wk * 2, plane_b = (cuuint64_t)w_rows * wk * 2;
+        const cuuint32_t pl = (cuuint32_t)planes;
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r;
-        if (p.wstat) {
-            // packed diagonal sub-blocks {16 K, coutp, 9 taps, plane}: the whole n-tile (64 rows x 9 taps) in one box, 32B swizzle
-            cuuint64_t d4[4] = {16, (cuuint64_t)coutp, (cuuint64_t)taps, (cuuint64_t)planes};
-            cuuint64_t s4[3] = {32, (cuuint64_t)coutp * 32, (cuuint64_t)taps * coutp * 32};
-            cuuint32_t b4[4] = {16u, 64u, 9u, (cuuint32_t)planes};
-            cuuint32_t e4[4] = {1, 1, 1, 1};
-            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_diag, d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else if (p.halo) {
-            // {K, coutp, taps, plane}: one box brings the 3 horizontal taps of a kernel row
-            cuuint64_t d4[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)taps, (cuuint64_t)planes};
-            cuuint64_t s4[3] = {wk * 2, (cuuint64_t)coutp * wk * 2, (cuuint64_t)w_rows * wk * 2};
-            cuuint32_t b4[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, 3u, (cuuint32_t)planes};
-            cuuint32_t e4[4] = {1, 1, 1, 1};
-            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (blockdiag && p.halo) {          // smem [3 taps][4 sub-blocks][plane][16 rows]
+            cuuint64_t d[5] = {wk, 16, (cuuint64_t)planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
+            cuuint64_t st[4] = {row_b, plane_b, 16 * row_b, (cuuint64_t)coutp * row_b};
+            cuuint32_t b[5] = {(cuuint32_t)BLOCK_K, 16u, pl, (cuuint32_t)block_n / 16, 3u};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else {
-            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        } else if (blockdiag) {             // smem [4 sub-blocks][plane][16 rows]
+            cuuint64_t d[4] = {wk, 16, (cuuint64_t)planes, (cuuint64_t)w_rows / 16};
+            cuuint64_t st[3] = {row_b, plane_b, 16 * row_b};
+            cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, 16u, pl, (cuuint32_t)block_n / 16};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else if (p.halo) {                // smem [3 taps][plane][block_n rows]: one box brings the 3 horizontal taps of a kernel row
+            cuuint64_t d[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)planes, (cuuint64_t)taps};
+            cuuint64_t st[3] = {row_b, plane_b, (cuuint64_t)coutp * row_b};
+            cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, pl, 3u};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {                            // smem [plane][block_n rows]
+            cuuint64_t d[3] = {wk, (cuuint64_t)w_rows, (cuuint64_t)planes};
+            cuuint64_t st[2] = {row_b, plane_b};
+            cuuint32_t b[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, pl};
+            r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
@@ -833,13 +825,14 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             res_tma_ok = true;
         }
     }
+    // a split residual under the TMA-store epilogue is either TMA-loaded (STG == 3) or register-prefetched (halo, <64,2,1>)
+    if (p.tma_out && res_split && !res_tma_ok && !p.halo) p.tma_out = 0;
     cudaStream_t st = (cudaStream_t)stream_;
     const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
     switch (block_n) {
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 64:
-            if (p.wstat && p.tma_out) return launch_tc<64, 3, 2>(tmA, tmB, tmO, tmR, p, st);
             if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, tmR, p, st);
             if (res_tma_ok) return launch_tc<64, 2, 3>(tmA, tmB, tmO, tmR, p, st);
             return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, tmR, p, st);
