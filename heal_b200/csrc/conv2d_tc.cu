@@ -43,6 +43,7 @@ struct TcP {
     int taps_w, taps, pad;        // kw, kh*kw, padding
     int stride;                   // conv stride (TMA element stride on W and H)
     int blockdiag;                // grouped conv as block-diagonal 64x64 channel blocks: n-tile nt reads channel block nt only
+    int bdiag;                    // block-diagonal weights arrive packed: only the four 16x16 diagonal sub-blocks ([16 rows][32 B], 32B swizzle)
     int kc_blocks;                // Cin / 64
     int TH, TW, tiles_h, tiles_w; // pixel tile and tile grid per image
     int m_tiles, n_tiles;
@@ -115,6 +116,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+// K-major, 32B-swizzled descriptor (rows of 32 B = 16 bf16, 8-row groups 256 B apart): the packed diagonal weight sub-blocks.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                           // SWIZZLE_32B
     return d;
 }
 
@@ -193,7 +205,8 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     extern __shared__ uint8_t smem_raw[];
     // 1024 B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    // weight bytes per (tap, plane) in a stage: a BLOCK_N x 64 tile, or (grouped, packed) the four 16x16 diagonal sub-blocks
+    const int B_TILE_BYTES = p.bdiag ? (BLOCK_N / 16) * 512 : BLOCK_N * BLOCK_K * 2;
     // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
     const int halo_a_plane = (p.TW + 2) * 128;
     const int halo_a_bytes = (p.planes * halo_a_plane + 1023) & ~1023;
@@ -325,15 +338,17 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 if (p.blockdiag) {
                                     // Grouped conv: channels-per-group divides 16, so output channels [16k,16k+16) of this 64-block depend
                                     // only on input channels [16k,16k+16): one M128 x N16 x K16 product per 16-channel sub-block.
-                                    const uint32_t bk = bs + k * sub_bytes + k * 32;            // sub-block k, K offset k*16 elements
+                                    // sub-block k: [plane][16 rows] of 128 B rows at K offset k*16 elements, or packed 32 B rows
+                                    const uint32_t bk = p.bdiag ? bs + k * p.planes * 512 : bs + k * sub_bytes + k * 32;
+                                    const uint64_t bd = p.bdiag ? umma_desc_sw32(bk) : umma_desc_sw128(bk);
                                     const uint32_t td = tmem_d + (uint32_t)(k * sub_cols);
                                     const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
                                     if constexpr (NCAT) {
                                         if (split) {
-                                            umma_bf16(td, a_hi, umma_desc_sw128(bk), idesc32, f0);      // [a_hi*b_hi | a_hi*b_lo]
-                                            umma_bf16(td, a_lo, umma_desc_sw128(bk), idesc16, 1u);      // += a_lo*b_hi
+                                            umma_bf16(td, a_hi, bd, idesc32, f0);      // [a_hi*b_hi | a_hi*b_lo]
+                                            umma_bf16(td, a_lo, bd, idesc16, 1u);      // += a_lo*b_hi
                                         } else {
-                                            umma_bf16(td, a_hi, umma_desc_sw128(bk), idesc16, f0);
+                                            umma_bf16(td, a_hi, bd, idesc16, f0);
                                         }
                                     }
                                 } else {
@@ -660,8 +675,9 @@ template <int BLOCK_N, int STAGES, int STG>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const TcP& p_in, cudaStream_t st) {
     TcP p = p_in;
     p.res_tma = (STG == 3 && p.tma_out && p.res_split) ? 1 : 0;
-    size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2);
-    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * BLOCK_N * BLOCK_K * 2;
+    const size_t b_tile = p.bdiag ? (size_t)(BLOCK_N / 16) * 512 : (size_t)BLOCK_N * BLOCK_K * 2;
+    size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + b_tile);
+    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * b_tile;
     size_t smem = 1024 + (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
@@ -757,7 +773,24 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         const cuuint32_t pl = (cuuint32_t)planes;
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r;
-        if (blockdiag && p.halo) {          // smem [3 taps][4 sub-blocks][plane][16 rows]
+        p.bdiag = (blockdiag && w_diag) ? 1 : 0;
+        if (p.bdiag) {
+            // packed diagonal sub-blocks in global memory: [plane][taps * coutp rows][16] bf16 (32 B rows) -> a quarter of the bytes
+            const cuuint64_t pb = (cuuint64_t)w_rows * 32;
+            if (p.halo) {                   // smem [3 taps][4 sub-blocks][plane][16 rows][32 B]
+                cuuint64_t d[5] = {16, 16, (cuuint64_t)planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
+                cuuint64_t st[4] = {32, pb, 512, (cuuint64_t)coutp * 32};
+                cuuint32_t b[5] = {16u, 16u, pl, (cuuint32_t)block_n / 16, 3u};
+                r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)w_diag, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            } else {                        // smem [4 sub-blocks][plane][16 rows][32 B]
+                cuuint64_t d[4] = {16, 16, (cuuint64_t)planes, (cuuint64_t)w_rows / 16};
+                cuuint64_t st[3] = {32, pb, 512};
+                cuuint32_t b[4] = {16u, 16u, pl, (cuuint32_t)block_n / 16};
+                r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_diag, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+        } else if (blockdiag && p.halo) {   // smem [3 taps][4 sub-blocks][plane][16 rows]
             cuuint64_t d[5] = {wk, 16, (cuuint64_t)planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
             cuuint64_t st[4] = {row_b, plane_b, 16 * row_b, (cuuint64_t)coutp * row_b};
             cuuint32_t b[5] = {(cuuint32_t)BLOCK_K, 16u, pl, (cuuint32_t)block_n / 16, 3u};
@@ -833,7 +866,9 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 64:
+            if (p.halo && p.bdiag && p.tma_out) return launch_tc<64, 4, 1>(tmA, tmB, tmO, tmR, p, st);     // 45 KiB stages
             if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, tmR, p, st);
+            if (p.bdiag && p.tma_out && !res_tma_ok) return launch_tc<64, 4, 2>(tmA, tmB, tmO, tmR, p, st);   // 36 KiB stages
             if (res_tma_ok) return launch_tc<64, 2, 3>(tmA, tmB, tmO, tmR, p, st);
             return p.tma_out ? launch_tc<64, 3, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         default:
