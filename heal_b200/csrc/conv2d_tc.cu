@@ -55,7 +55,7 @@ struct TcP {
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
     int halo;                     // 3x3 stride-1, one-row tiles: ONE activation load per kernel ROW (TW+2 pixels) serves the 3 horizontal taps
     int tma_out;                  // epilogue drains through shared memory + TMA tensor store (tmO valid)
-    int res_tma;                  // STG == 3: the residual chunk is TMA-loaded into the staging buffer one chunk ahead (tmR valid)
+    int res_tma;                  // STG >= 2: the residual chunk is TMA-loaded into the staging buffer one chunk ahead (tmR valid)
     int dbg;                      // HEAL_TC_DBG experiment bits (timing only, results invalid): 1 no stores, 2 no B loads, 4 no A loads, 8 no residual loads (TMA-store epilogue), 16 no MMAs
     const float* bias;            // [Cout]
     // residual (optional): split planes or fp32
@@ -202,9 +202,15 @@ template <int BLOCK_N, int STAGES, int STG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcP p) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024 B alignment for the 128B swizzle atoms
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024 B alignment for the 128B swizzle atoms: requested from the toolchain (no slack bytes to round up inside -- the halo +
+    // two-staging-buffer configuration needs all 227 KiB) and checked once.  The pointer is laundered through an empty asm so
+    // that shared-memory addresses stay run-time values: with compile-time-constant addresses ptxas emits a slower kernel
+    // (measured A/B on one box: level-0 1x1 conv 51 -> 66 us).
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uintptr_t raw_addr = reinterpret_cast<uintptr_t>(smem_raw);
+    asm volatile("" : "+l"(raw_addr));
+    uint8_t* smem = reinterpret_cast<uint8_t*>(raw_addr);
+    if (smem_u32(smem) & 1023u) __trap();
     // weight bytes per (tap, plane) in a stage: a BLOCK_N x 64 tile, or (grouped, packed) the four 16x16 diagonal sub-blocks
     const int B_TILE_BYTES = p.bdiag ? (BLOCK_N / 16) * 512 : BLOCK_N * BLOCK_K * 2;
     // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
@@ -419,7 +425,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         };
         uint4 rn_h[4], rn_l[4];
-        const bool res_tma = (STG == 3) && p.res_tma && !(p.dbg & 8);
+        // compiled only into the instantiations that are dispatched with a residual (<*,2,3> and the halo <64,2,2>): the extra
+        // single-thread TMA issue path costs the others ~800 R2UR moves and 5-40 % of their speed (measured A/B on one box)
+        constexpr bool RES_TMA_OK = (STG == 3) || (STG == 2 && BLOCK_N == 64 && STAGES == 2);
+        const bool res_tma = RES_TMA_OK && p.res_tma && !(p.dbg & 8);
         constexpr bool RES_PF = (STG == 1 && BLOCK_N == 64);      // the halo configuration: no room for 3 staging buffers
         const bool res_pf = RES_PF && p.tma_out && p.res_split && !(p.dbg & 8);
         auto res_fetch = [&](int tile_, int c64_) {
@@ -471,9 +480,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
                     const int b = stg_count % STG;
                     if (res_tma) {
-                        // (A') store(i-2) has left buffer (i+1) % 3 -> request residual(i+1) into it, then wait for residual(i) in buffer b
+                        // (A') the store that last used buffer (i+1) % STG has been read out -> request residual(i+1) into it, then wait
+                        // for residual(i) in buffer b (STG == 3: a full chunk of lead; STG == 2: the lead is the chunk minus the store drain)
                         if (warp == 2 && lane == 0) {
-                            bulk_wait_read<1>();
+                            bulk_wait_read<(STG >= 2 ? STG - 2 : 0)>();
                             int ntile = tile, nc = c64 + 1;
                             if (nc == BLOCK_N / 64) { nc = 0; ntile = tile + (int)gridDim.x; }
                             if (ntile < total_tiles) res_tma_issue(ntile, nc, (stg_count + 1) % STG);
@@ -674,11 +684,11 @@ PFN_tmEncodeTiled get_encode() {
 template <int BLOCK_N, int STAGES, int STG>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const TcP& p_in, cudaStream_t st) {
     TcP p = p_in;
-    p.res_tma = (STG == 3 && p.tma_out && p.res_split) ? 1 : 0;
+    p.res_tma = ((STG == 3 || (STG == 2 && BLOCK_N == 64 && STAGES == 2)) && p.tma_out && p.res_split && p_in.res_tma) ? 1 : 0;
     const size_t b_tile = p.bdiag ? (size_t)(BLOCK_N / 16) * 512 : (size_t)BLOCK_N * BLOCK_K * 2;
     size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + b_tile);
     if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * b_tile;
-    size_t smem = 1024 + (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
+    size_t smem = (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -728,6 +738,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     if (!enc) return HEAL_ERR_DRIVER;
 
     TcP p;
+    p.res_tma = 0; p.bdiag = 0;
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.taps_w = kw; p.taps = taps; p.pad = pad; p.kc_blocks = Cin / BLOCK_K;
     int tw = 128; while (tw > Wo && tw > 8) tw >>= 1;
@@ -844,7 +855,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     {
         const char* e = getenv("HEAL_TC_RES_TMA");
         const bool want = !(e && atoi(e) == 0);
-        if (want && p.tma_out && res_split && !p.halo) {
+        if (want && p.tma_out && res_split) {
             cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N, (cuuint64_t)planes};
             cuuint64_t strides[4] = {(cuuint64_t)res_cstride * 2, (cuuint64_t)Wo * res_cstride * 2, (cuuint64_t)Ho * Wo * res_cstride * 2,
                                      (cuuint64_t)res_plane_stride * 2};
@@ -856,16 +867,19 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
             res_tma_ok = true;
+            p.res_tma = 1;
         }
     }
     // a split residual under the TMA-store epilogue is either TMA-loaded (STG == 3) or register-prefetched (halo, <64,2,1>)
     if (p.tma_out && res_split && !res_tma_ok && !p.halo) p.tma_out = 0;
+    if (p.halo && p.bdiag) p.res_tma = 0;      // <64,4,1>: register prefetch
     cudaStream_t st = (cudaStream_t)stream_;
     const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
     switch (block_n) {
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 64:
+            if (p.halo && res_tma_ok && !p.bdiag) return launch_tc<64, 2, 2>(tmA, tmB, tmO, tmR, p, st);   // 81 KiB stages + 2 x 32 KiB: all of shared memory
             if (p.halo && p.bdiag && p.tma_out) return launch_tc<64, 4, 1>(tmA, tmB, tmO, tmR, p, st);     // 45 KiB stages
             if (p.halo) return p.tma_out ? launch_tc<64, 2, 1>(tmA, tmB, tmO, tmR, p, st) : launch_tc<64, 2, 0>(tmA, tmB, tmO, tmR, p, st);
             if (p.bdiag && p.tma_out && !res_tma_ok) return launch_tc<64, 4, 2>(tmA, tmB, tmO, tmR, p, st);   // 36 KiB stages

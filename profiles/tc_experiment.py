@@ -17,7 +17,10 @@ SHAPES = [("shrink3x3_384_256_n1", 384, 256, 3, 1, 1), ("res3x3_64_64_n5_res", 6
 
 def main():
     from heal_b200 import ops
+    only = os.environ.get("TC_EXP_ONLY")
     for name, cin, cout, k, groups, N in SHAPES:
+        if only and only not in name:
+            continue
         H = W = 64 if "64px" in name else (128 if "128px" in name else 256)
         conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2, groups=groups, bias=False)
         pc = ops.pack_conv_tc(conv, torch.nn.BatchNorm2d(cout).eval(), True, planes=2).to("cuda")
