@@ -494,73 +494,78 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (warp == 2 && lane == 0) bulk_wait_read<STG - 1>();
                         epi_bar(1);
                     }
-                    // (B) this warp's 32 columns of the 64-column chunk -> registers -> epilogue -> swizzled smem
+                    // (B) this warp's 32 columns of the 64-column chunk -> registers -> epilogue -> swizzled smem.  Loads first (bias:
+                    // warp-uniform 16 B broadcasts; residual: this thread's eight 16 B slots of the staging buffer), then the
+                    // arithmetic, then the eight 16 B stores back to back.
                     uint32_t raw[32];
                     const int col0 = c64 * 64 + chalf * 32;
-                    ld_acc(col0, raw);
-                    bool pre = false;
-                    if (RES_PF && res_pf) {
-                        // fold bias + residual (prefetched one chunk ago) into raw, then reuse the registers for the next chunk's request
+                    float bv[32];
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            const int c = ch0 + col0 + g8 * 8;
-                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rn_h[g8]);
-                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rn_l[g8]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float v = __uint_as_float(raw[g8 * 8 + j]) + ((p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
-                                v += __bfloat162float(hb[j]);
-                                if (p.planes == 2) v += __bfloat162float(lb[j]);
-                                raw[g8 * 8 + j] = __float_as_uint(v);
-                            }
-                        }
-                        pre = true;
-                        if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
-                        else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
+                    for (int g = 0; g < 8; ++g) {
+                        float4 t = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + col0) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        bv[4 * g] = t.x; bv[4 * g + 1] = t.y; bv[4 * g + 2] = t.z; bv[4 * g + 3] = t.w;
                     }
                     const uint32_t srow = stg_base + b * stg_bytes + row * 128;
+                    uint4 rh[4], rl[4];
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) { rh[g8] = make_uint4(0u, 0u, 0u, 0u); rl[g8] = make_uint4(0u, 0u, 0u, 0u); }
+                    bool have_res = false;
+                    if (res_tma) {
+                        have_res = true;
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rh[g8].x), "=r"(rh[g8].y), "=r"(rh[g8].z), "=r"(rh[g8].w) : "r"(srow + chunk16));
+                            if (p.planes == 2)
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rl[g8].x), "=r"(rl[g8].y), "=r"(rl[g8].z), "=r"(rl[g8].w) : "r"(srow + A_TILE_BYTES + chunk16));
+                        }
+                    } else if (RES_PF && res_pf) {
+                        have_res = true;        // register-prefetched one chunk ago (rn_h / rn_l)
+                    }
+                    const uint4* res_h = RES_PF ? rn_h : rh;
+                    const uint4* res_l = RES_PF ? rn_l : rl;
+                    ld_acc(col0, raw);
+                    uint32_t hw[4][4], lw[4][4];
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
                         const int c = ch0 + col0 + g8 * 8;
                         float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + ((!pre && p.bias && c + j < p.Cout) ? __ldg(p.bias + c + j) : 0.f);
-                        const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
-                        if (res_tma) {
-                            uint4 h, l = make_uint4(0u, 0u, 0u, 0u);
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(srow + chunk16) : "memory");
-                            if (p.planes == 2)
-                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(srow + A_TILE_BYTES + chunk16) : "memory");
-                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
-                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g8 * 8 + j]) + bv[g8 * 8 + j];
+                        if (have_res) {
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&res_h[g8]);
+                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&res_l[g8]);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(hb[j]);
                             if (p.planes == 2) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(lb[j]);
                             }
-                        } else if (pre) {
-                            // bias + residual already folded into raw
-                        } else if (valid && c + 8 <= p.Cout && !(p.dbg & 8)) {
-                            if (p.res_f32) {
-                                const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
+                        } else if (valid && p.res_f32 && !(p.dbg & 8)) {
+                            const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
-                            }
+                            for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
                         }
                         if (p.relu) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                         }
                         float lo[8];
-                        uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { hw[j] = pack_bf16(v[2 * j], v[2 * j + 1]); lw[j] = pack_bf16(lo[2 * j], lo[2 * j + 1]); }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk16), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+                        for (int j = 0; j < 4; ++j) { hw[g8][j] = pack_bf16(v[2 * j], v[2 * j + 1]); lw[g8][j] = pack_bf16(lo[2 * j], lo[2 * j + 1]); }
+                    }
+                    if (RES_PF && res_pf) {      // registers consumed: request the next chunk's residual
+                        if (c64 + 1 < BLOCK_N / 64) res_fetch(tile, c64 + 1);
+                        else if (tile + (int)gridDim.x < total_tiles) res_fetch(tile + gridDim.x, 0);
+                    }
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const uint32_t chunk16 = (uint32_t)(((chalf * 4 + g8) ^ (row & 7)) * 16);      // 128B swizzle
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk16), "r"(hw[g8][0]), "r"(hw[g8][1]), "r"(hw[g8][2]), "r"(hw[g8][3]) : "memory");
                         if (p.planes == 2)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + A_TILE_BYTES + chunk16), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + A_TILE_BYTES + chunk16), "r"(lw[g8][0]), "r"(lw[g8][1]), "r"(lw[g8][2]), "r"(lw[g8][3]) : "memory");
                     }
                     fence_async_smem();
                     epi_bar(2);
