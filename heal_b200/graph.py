@@ -50,3 +50,78 @@ class FrameGraph:
     def replay(self):
         self.graph.replay()
         return self.out
+
+
+class FramePipeline:
+    """Two captured frames on three streams: while frame i computes, frame i+1's inputs are copied in (pinned host -> HBM) and
+    frame i-1's predictions are copied out (HBM -> pinned host).  The serving loop's public entry point:
+
+        pipe = FramePipeline(model, n_agents, point_capacity, pairwise_shape)
+        preds = pipe.submit(points_pinned, offsets_pinned, pairwise_pinned)   # dict of pinned host tensors of frame i - 1 (or None)
+        last = pipe.flush()                                                      # waits for the frame in flight
+
+    Each frame's result is complete on the host before its buffers are reused (events, no host sync inside submit).
+    """
+
+    OUT_KEYS = ("cls_preds", "reg_preds", "dir_preds")
+
+    def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, modality: str = "m1", device=None):
+        dev = device or next(model.parameters()).device
+        self.dev = dev
+        self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(2)]
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.host_out = [{k: torch.empty(g.out[k].shape, dtype=g.out[k].dtype).pin_memory() for k in self.OUT_KEYS if k in g.out}
+                         for g in self.graphs]
+        self.count = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
+        cur = torch.cuda.current_stream(dev)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.wait_stream(cur)
+
+    def submit(self, points: torch.Tensor, offsets: torch.Tensor, pairwise: torch.Tensor):
+        k = self.count & 1
+        g = self.graphs[k]
+        prev = None
+        with torch.cuda.stream(self.s_in):
+            if self.count >= 2:
+                self.s_in.wait_event(self.ev_comp[k])          # frame count-2 has consumed these input buffers
+            g.load(points, offsets, pairwise)
+            self.ev_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(self.ev_in[k])
+            if self.count >= 2:
+                self.s_comp.wait_event(self.ev_out[k])         # its predictions have left the output buffers
+            g.replay()
+            self.ev_comp[k].record(self.s_comp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_comp[k])
+            for name, h in self.host_out[k].items():
+                h.copy_(g.out[name], non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        if self.count >= 1:
+            self.ev_out[k ^ 1].synchronize()                   # frame count-1 is complete on the host
+            prev = self.host_out[k ^ 1]
+        self.h2d_bytes = points.numel() * points.element_size() + offsets.numel() * offsets.element_size() \
+            + pairwise.numel() * pairwise.element_size()
+        self.count += 1
+        return prev
+
+    def flush(self):
+        if self.count == 0:
+            return None
+        k = (self.count - 1) & 1
+        self.ev_out[k].synchronize()
+        return self.host_out[k]
+
+    def join(self, begin: bool):
+        """Order the pipeline's streams after (begin) / before (end) the caller's current stream, e.g. around timing events."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            if begin:
+                s.wait_stream(cur)
+            else:
+                cur.wait_stream(s)

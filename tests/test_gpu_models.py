@@ -120,3 +120,45 @@ def test_agent_sharded_world1_equals_plain_forward():
         b = parallel.forward_agent_sharded(model, data, 0, 1)
     for k in ("cls_preds", "reg_preds", "dir_preds"):
         torch.testing.assert_close(a[k], b[k], rtol=0, atol=0)
+
+
+def test_frame_graph_and_pipeline_equal_eager():
+    """CUDA-graph replay (FrameGraph) and the 3-stream serving loop (FramePipeline: copy-in / compute / copy-out overlap, two
+    captured frames) return, frame by frame, exactly what the eager module call returns for clouds of different sizes."""
+    from heal_b200 import synth
+    from heal_b200.graph import FrameGraph, FramePipeline
+    args = make_golden.small_model_args()
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "heter_pyramid_collab_small.pt"), weights_only=False)
+    model, _ = _build(args, g["shapes"])
+    scenes = []
+    for seed, az in ((3, 256), (4, 192), (5, 320), (6, 256), (7, 224)):
+        sc = synth.scene(seed, n_agents=3, rings=16, azimuth=az)
+        offs = np.concatenate([[0], np.cumsum([p.shape[0] for p in sc["points"]])]).astype(np.int32)
+        scenes.append((torch.from_numpy(np.concatenate(sc["points"])).pin_memory(), torch.from_numpy(offs).pin_memory(),
+                       torch.from_numpy(sc["pairwise_t_matrix"]).pin_memory()))
+    keys = ("cls_preds", "reg_preds", "dir_preds")
+    eager = []
+    with torch.no_grad():
+        for p, o, pw in scenes:
+            out = model({"inputs_m1": {"points": p.cuda(), "agent_offsets": o.cuda()}, "agent_modality_list": ["m1"] * 3,
+                         "record_len": torch.tensor([3]), "pairwise_t_matrix": pw.cuda()})
+            eager.append({k: out[k].cpu().clone() for k in keys})
+    cap = (max(s[0].shape[0] for s in scenes) + 4095) // 4096 * 4096
+    fg = FrameGraph(model, 3, cap, tuple(scenes[0][2].shape))
+    assert fg.kernels_per_replay > 0
+    for i, (p, o, pw) in enumerate(scenes):
+        fg.load(p, o, pw)
+        out = fg.replay()
+        for k in keys:
+            assert torch.equal(out[k].cpu(), eager[i][k]), (i, k)
+    pipe = FramePipeline(model, 3, cap, tuple(scenes[0][2].shape))
+    got = []
+    for p, o, pw in scenes:
+        prev = pipe.submit(p, o, pw)
+        if prev is not None:
+            got.append({k: prev[k].clone() for k in keys})
+    got.append({k: pipe.flush()[k].clone() for k in keys})
+    assert len(got) == len(scenes)
+    for i in range(len(scenes)):
+        for k in keys:
+            assert torch.equal(got[i][k], eager[i][k]), (i, k)
