@@ -28,6 +28,7 @@ SIGNATURES = {
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _ap, _vp]),
     "heal_pillar_idmap": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "heal_sparse_stem": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _ap, _ap, _vp]),
+    "heal_sparse_stem_tc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _ap, _ap, _vp]),
     "heal_conv2d_simt": (_i, [_ap, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _ap, _ap, _i, _i, _i,
                               _i, _i, _i, _i, _vp]),
     "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i,

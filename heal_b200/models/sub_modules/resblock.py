@@ -46,7 +46,8 @@ class BasicBlock(nn.Module):
             if engine.SPARSE_STEM and self._stem_eligible() and x.H % 2 == 0 and x.W % 2 == 0:
                 # scatter + conv1/bn1/ReLU + downsample/bn in one kernel, straight from the pillar list
                 y, idt = ops.sparse_stem(x, engine.packed(self.conv1, self.bn1, True, kind="simt"),
-                                         engine.packed(self.downsample[0], self.downsample[1], False, kind="simt"), engine.act_fmt())
+                                         engine.packed(self.downsample[0], self.downsample[1], False, kind="simt"), engine.act_fmt(),
+                                         tensor_cores=(engine.STEM_TC and engine.PRECISION != "fp32"))
                 return conv_bn_act(y, self.conv2, self.bn2, relu=True, residual=idt, out=out)
             from ...engine import act_fmt
             x = x.dense(act_fmt())

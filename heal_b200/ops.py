@@ -711,15 +711,17 @@ def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, 
     return SparseCanvas(pf, idmap, batch_size, ny, nx, densify)
 
 
-def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_fmt: str):
-    """BasicBlock.conv1(3x3 s2 p1)+bn1+ReLU and downsample(1x1 s2)+bn from the pillar list. Returns (Act conv, Act down)."""
+def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_fmt: str, tensor_cores: bool = False):
+    """BasicBlock.conv1(3x3 s2 p1)+bn1+ReLU and downsample(1x1 s2)+bn from the pillar list. Returns (Act conv, Act down).
+    tensor_cores: split-bf16 mma.sync variant (fp32-equivalent; the tc32 / bf16 engine modes), else fp32 FMAs."""
     assert pc_conv.kh == 3 and pc_conv.stride == 2 and pc_conv.pad == 1 and pc_conv.cin == 64 and pc_conv.cout == 64 and pc_conv.relu
     assert pc_down.kh == 1 and pc_down.stride == 2 and pc_down.pad == 0 and pc_down.cin == 64 and pc_down.cout == 64 and not pc_down.relu
     o1 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
     o2 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
     v1, v2 = o1.view(), o2.view()
+    fn = lib.heal_sparse_stem_tc if (tensor_cores and sc.W % 32 == 0) else lib.heal_sparse_stem
     with _Prof("sparse_stem", 0):
-        rc = lib.heal_sparse_stem(_p(sc.feats), _p(sc.idmap), sc.N, sc.H, sc.W, _p(pc_conv.weight), _p(pc_conv.bias),
-                                  _p(pc_down.weight), _p(pc_down.bias), 64, ctypes.byref(v1), ctypes.byref(v2), _stream())
+        rc = fn(_p(sc.feats), _p(sc.idmap), sc.N, sc.H, sc.W, _p(pc_conv.weight), _p(pc_conv.bias),
+                _p(pc_down.weight), _p(pc_down.bias), 64, ctypes.byref(v1), ctypes.byref(v2), _stream())
     check(rc, "heal_sparse_stem")
     return o1, o2

@@ -93,6 +93,11 @@ int heal_pillar_idmap(const int* voxel_coords, const int* num_voxels_dev, int nu
 int heal_sparse_stem(const float* pillar_features, const int* idmap, int batch, int ny, int nx,
                      const float* w_conv3x3, const float* b_conv3x3, const float* w_down1x1, const float* b_down1x1,
                      int channels, const heal_act_t* out_conv, const heal_act_t* out_down, void* stream);
+/* Same contract on the tensor cores (mma.sync m16n8k16, split-bf16 hi/lo operands: fp32-equivalent, ~1e-6 relative, not
+ * bit-identical to the fp32 FMA order); needs nx % 32 == 0.  A warp owns 16 output pixels, all ten weight matrices stay in smem. */
+int heal_sparse_stem_tc(const float* pillar_features, const int* idmap, int batch, int ny, int nx,
+                        const float* w_conv3x3, const float* b_conv3x3, const float* w_down1x1, const float* b_down1x1,
+                        int channels, const heal_act_t* out_conv, const heal_act_t* out_down, void* stream);
 
 /* ---- 2-D convolution, fp32 CUDA-core path ---------------------------------------------------
  * replaces nn.Conv2d / nn.ConvTranspose2d(k==stride) + eval BatchNorm2d + ReLU (+ residual add) of

@@ -227,13 +227,15 @@ def test_warp_att_golden(golden_dir):
     torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), g["att"][0], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tc32"])
+@pytest.mark.parametrize("prec", ["fp32", "tc32", "tc32-mma"])
 def test_sparse_stem_equals_dense_canvas_path(prec):
     """scatter + first residual block straight from the pillar list == the same block on the materialised canvas."""
     from heal_b200 import ops, synth, engine
     from heal_b200.models.sub_modules.resblock import BasicBlock, conv1x1
     from oracle import procedural
-    old = engine.PRECISION
+    old, old_tc = engine.PRECISION, engine.STEM_TC
+    engine.STEM_TC = prec.endswith("-mma")          # heal_sparse_stem_tc (mma.sync, split-bf16) instead of the fp32 gather kernel
+    prec = prec.split("-")[0]
     engine.set_precision(prec)
     try:
         sc = synth.scene(9, n_agents=2, rings=32, azimuth=512)
@@ -264,4 +266,5 @@ def test_sparse_stem_equals_dense_canvas_path(prec):
         assert err < tol, (err, tol, scale)
     finally:
         engine.SPARSE_STEM = True
+        engine.STEM_TC = old_tc
         engine.set_precision(old)
