@@ -436,6 +436,14 @@ def main():
                         "tensor_pipe_frac": ach * mma_per_flop / peak_tf if ach else None,
                         "ms_per_frame": ms, "share_of_step": ms / (total_ms / opt.steps),
                         "all_kernels": prof}
+            # the same launches against the HBM roof: DRAM bytes per launch (ncu, `traffic`) over the live average launch time
+            hbm_peak = peaks.get("hbm_gbs", 6577.0) if peaks else 6577.0
+            if traffic and nl and ms > 0:
+                gbps = traffic / (1e-3 * ms / nl) / 1e9
+                roofline["hbm"] = {"achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                                   "note": "DRAM bytes per launch (profiles/ncu_traffic_r1.json) / average live launch duration; the frame's "
+                                           "conv launches split into HBM-bound 1x1 / grouped ones and MMA-bound 3x3 ones, so neither "
+                                           "fraction alone reaches 1"}
         cpu = None
         if not opt.no_cpu_baseline:
             cores = pick_host_threads()
