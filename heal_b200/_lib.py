@@ -36,6 +36,9 @@ SIGNATURES = {
     "heal_pyramid_fuse_level": (_i, [_ap, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ap, _vp]),
     "heal_att_fuse": (_i, [_ap, _vp, _i, _i, _i, _i, _ap, _vp]),
     "heal_act_convert": (_i, [_ap, _ap, _sz, _i, _vp]),
+    "heal_postprocess_workspace": (_sz, [_i, _i, _i, _i]),
+    "heal_box_decode_nms": (_i, [_ap, _ap, _ap, _vp, _i, _i, _i, _c.c_float, _c.c_float, _i, _vp, _i, _c.c_float, _i,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_spconv_table_size": (_sz, [_i]),
     "heal_spconv_build_table": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "heal_spconv_subm_neighbors": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

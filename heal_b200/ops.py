@@ -725,3 +725,57 @@ def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_
                 _p(pc_down.weight), _p(pc_down.bias), 64, ctypes.byref(v1), ctypes.byref(v2), _stream())
     check(rc, "heal_sparse_stem")
     return o1, o2
+
+
+# ------------------------------------------------------------------------------------------------
+# detection post-processing (box decode + score filter + rotated NMS), SURVEY 8f rank 1
+# ------------------------------------------------------------------------------------------------
+class PostprocessBuffers:
+    """Caller-owned outputs + workspace of heal_box_decode_nms for one (H, W, anchors, top) geometry (reusable, graph-safe)."""
+
+    def __init__(self, H: int, W: int, A: int, top: int, device):
+        self.H, self.W, self.A, self.top = H, W, A, top
+        nbytes = int(lib.heal_postprocess_workspace(H, W, A, top))
+        if nbytes == 0:
+            raise ValueError("bad post-processing geometry")
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        self.boxes = torch.zeros((top, 8, 3), dtype=torch.float32, device=device)
+        self.scores = torch.zeros((top,), dtype=torch.float32, device=device)
+        self.count = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.stats = torch.zeros((2,), dtype=torch.int32, device=device)
+
+
+def _head_act(t) -> Act:
+    """Accept an Act (f32) or a logical-NCHW fp32 tensor (any strides; channels-last storage is used as is)."""
+    if isinstance(t, Act):
+        assert t.fmt == "f32"
+        return t
+    return to_act(t)
+
+
+def box_decode_nms(cls_preds, reg_preds, dir_preds, anchors: torch.Tensor, transform, score_threshold: float, nms_threshold: float,
+                   dir_offset: float = 0.0, num_bins: int = 2, order: str = "hwl", gt_range=None, top: int = 1000,
+                   buffers: Optional[PostprocessBuffers] = None) -> PostprocessBuffers:
+    """VoxelPostprocessor.post_process for one cav on the GPU (no host sync): heads (1,A,H,W) / (1,7A,H,W) / (1,A*bins,H,W) or None,
+    anchors (H,W,A,7) fp32 device, transform 4x4 (host values).  Returns the buffers: boxes[:count], scores[:count] in pick order."""
+    c, r = _head_act(cls_preds), _head_act(reg_preds)
+    d = _head_act(dir_preds) if dir_preds is not None else None
+    assert c.N == 1 and r.N == 1 and r.C == 7 * c.C and (d is None or d.C == c.C * num_bins)
+    H, W, A = c.H, c.W, c.C
+    _need_cuda(anchors)
+    assert anchors.dtype == torch.float32 and anchors.is_contiguous() and anchors.numel() == H * W * A * 7
+    if buffers is None:
+        buffers = PostprocessBuffers(H, W, A, top, anchors.device)
+    assert (buffers.H, buffers.W, buffers.A, buffers.top) == (H, W, A, top)
+    T = _host_f32(np.asarray(torch.as_tensor(transform).detach().cpu().numpy(), dtype=np.float64).reshape(16))
+    rng = _host_f32(gt_range) if gt_range is not None else None
+    cv, rv = c.view(), r.view()
+    dv = d.view() if d is not None else None
+    with _Prof("box_decode_nms", 0):
+        rc = lib.heal_box_decode_nms(ctypes.byref(cv), ctypes.byref(rv), ctypes.byref(dv) if dv is not None else None, _p(anchors),
+                                     H, W, A, float(score_threshold), float(np.float32(dir_offset)), int(num_bins), T,
+                                     1 if order == "hwl" else 0, float(nms_threshold), int(top), rng,
+                                     _p(buffers.boxes), _p(buffers.scores), _p(buffers.count), _p(buffers.stats),
+                                     _p(buffers.workspace), buffers.workspace.numel(), _stream())
+    check(rc, "heal_box_decode_nms")
+    return buffers

@@ -202,6 +202,24 @@ int heal_spconv_gather_gemm(const float* in_feats, const int* nbr, const int* ou
 int heal_sparse_to_bev(const float* feats, const int* coords, const int* rows_dev, int capacity, int C, int D, int H, int W,
                        float* bev_out, void* stream);
 
+/* ---- detection post-processing ---------------------------------------------------------------
+ * replaces VoxelPostprocessor.post_process for one cav (voxel_postprocessor.py:245-405): sigmoid + score threshold,
+ * delta_to_boxes3d (:408-453), direction-bin fix (:314-330), boxes_to_corners_3d + project_box3d (box_utils.py:152-204, 278-316),
+ * remove_large_pred_bbx / remove_bbx_abnormal_z (:840-890), nms_rotated on the `top` best scores (:693-738, polygon IoU in
+ * fp64), mask_boxes_outside_range_numpy (:384-421).  Everything stays on the device and on the caller's stream.
+ *   cls (1,H,W,A) logits, reg (1,H,W,7A) deltas, dir (1,H,W,A*num_bins) or NULL: fp32 channels-last views (heal_act_t fmt 0)
+ *   anchors: device fp32 (H,W,A,7) [x y z h w l yaw] ('hwl' order, order_hwl = 1) or [x y z l w h yaw]
+ *   transform4x4_host: row-major cav -> ego matrix; range6_host: [minx miny minz maxx maxy maxz] or NULL (no range mask)
+ *   boxes_out (top,8,3) fp32, scores_out (top) fp32 in pick (score) order, count_out: device int = number of boxes written
+ *   stats_out: device int[2] = anchors above the score threshold, after the size / z filters (NULL allowed)
+ *   workspace >= heal_postprocess_workspace(H, W, A, top) bytes; top <= 2048 (the reference uses 1000) */
+size_t heal_postprocess_workspace(int H, int W, int anchors_per_cell, int top);
+int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal_act_t* dir, const float* anchors,
+                        int H, int W, int anchors_per_cell, float score_threshold, float dir_offset, int num_bins,
+                        const float* transform4x4_host, int order_hwl, float nms_threshold, int top,
+                        const float* range6_host, float* boxes_out, float* scores_out, int* count_out, int* stats_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- format conversion between fp32 and (split-)bf16 channels-last buffers ------------------- */
 int heal_act_convert(const heal_act_t* src, const heal_act_t* dst, size_t num_pixels, int channels, void* stream);
 

@@ -179,8 +179,74 @@ def main():
                 "out": {k: bout[k] for k in ("cls_preds", "reg_preds", "dir_preds")}},
                os.path.join(OUT, "heter_model_baseline_att_small.pt"))
     print("heter_model_baseline_att_small:", {k: tuple(v.shape) for k, v in bout.items() if torch.is_tensor(v)})
+    make_postprocess_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+def postprocess_params(rng=(-25.6, -25.6, -3, 25.6, 25.6, 1), voxel=(0.4, 0.4, 4)):
+    """`postprocess:` block of opv2v/MoreModality/HEAL/stage1/m1_pyramid.yaml:67-88 with the anchor grid that
+    yaml_utils.load_point_pillar_params (:121-135) derives, on a small range."""
+    import math
+    rng = list(rng)
+    return {"core_method": "VoxelPostprocessor", "gt_range": rng,
+            "anchor_args": {"cav_lidar_range": rng, "l": 3.9, "w": 1.6, "h": 1.56, "r": [0, 90], "feature_stride": 2, "num": 2,
+                            "vw": voxel[0], "vh": voxel[1], "vd": voxel[2],
+                            "W": math.ceil((rng[3] - rng[0]) / voxel[0]), "H": math.ceil((rng[4] - rng[1]) / voxel[1]),
+                            "D": math.ceil((rng[5] - rng[2]) / voxel[2])},
+            "target_args": {"pos_threshold": 0.6, "neg_threshold": 0.45, "score_threshold": 0.2},
+            "order": "hwl", "max_num": 150, "nms_thresh": 0.15,
+            "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}
+
+
+def postprocess_inputs(params, seed=3, logit_mean=-3.0):
+    """seeded head outputs: ~14 % of the anchors above the score threshold (more than the NMS's top-1000 cut on the 64x64 map),
+    deltas small enough that neighbouring boxes overlap, a rigid ego transform."""
+    g = torch.Generator().manual_seed(seed)
+    aa = params["anchor_args"]
+    h, w = aa["H"] // aa["feature_stride"], aa["W"] // aa["feature_stride"]
+    cls = logit_mean + 1.5 * torch.randn((1, 2, h, w), generator=g)
+    reg = 0.3 * torch.randn((1, 14, h, w), generator=g)
+    reg[:, 2::7] *= 0.3                                    # z delta: keep most boxes inside [-3, 1]
+    dirp = torch.randn((1, 4, h, w), generator=g)
+    yaw = 0.3
+    T = torch.tensor([[np.cos(yaw), -np.sin(yaw), 0, 1.5], [np.sin(yaw), np.cos(yaw), 0, -0.7], [0, 0, 1, 0.1], [0, 0, 0, 1]],
+                     dtype=torch.float32)
+    return cls, reg, dirp, T
+
+
+def make_postprocess_golden():
+    """UNMODIFIED reference VoxelPostprocessor.post_process (voxel_postprocessor.py:245-405).  shapely is absent: the reference's
+    `from shapely.geometry import Polygon` resolves to oracle.postprocess.QuadPolygon (see that file's header); the cython
+    opencood.utils.box_overlaps (training labels only) is stubbed."""
+    import types
+    from unittest.mock import MagicMock
+    from oracle import postprocess as opp
+    sg = types.ModuleType("shapely.geometry")
+    sg.Polygon = opp.QuadPolygon
+    sh = types.ModuleType("shapely")
+    sh.geometry = sg
+    sys.modules["shapely"], sys.modules["shapely.geometry"] = sh, sg
+    sys.modules.setdefault("opencood.utils.box_overlaps", MagicMock())
+    for m in [k for k in sys.modules if k.startswith("opencood.utils.common_utils") or k.startswith("opencood.utils.box_utils")]:
+        del sys.modules[m]
+    ref_shim.install()
+    from opencood.data_utils.post_processor.voxel_postprocessor import VoxelPostprocessor
+    import opencood.utils.common_utils as cu
+    assert cu.Polygon is opp.QuadPolygon
+    params = postprocess_params()
+    pp = VoxelPostprocessor(copy.deepcopy(params), train=False)
+    anchors = torch.from_numpy(pp.generate_anchor_box())
+    cases = {}
+    for name, seed, mean in (("dense", 3, -3.0), ("sparse", 4, -6.0)):
+        cls, reg, dirp, T = postprocess_inputs(params, seed, mean)
+        data = {"ego": {"transformation_matrix": T, "anchor_box": anchors}}
+        out = {"ego": {"cls_preds": cls.clone(), "reg_preds": reg.clone(), "dir_preds": dirp.clone()}}
+        with torch.no_grad():
+            boxes, scores = pp.post_process(data, out)
+        cases[name] = {"cls": cls, "reg": reg, "dir": dirp, "T": T, "boxes": boxes, "scores": scores}
+        print("postprocess", name, "candidates", int((torch.sigmoid(cls) > 0.2).sum()), "-> kept", 0 if boxes is None else boxes.shape[0])
+    torch.save({"params": params, "anchors": anchors, "cases": cases}, os.path.join(OUT, "postprocess.pt"))
 
 
 if __name__ == "__main__":
