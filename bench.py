@@ -389,6 +389,39 @@ def main():
             prof = {k: {"ms_per_frame": v[0] / 2, "gflop_per_frame": v[1] / 2 / 1e9, "launches_per_frame": v[2] / 2,
                         "tflops": (v[1] / 1e12) / (v[0] / 1e3) if v[0] > 0 else None} for k, v in agg.items()}
 
+        # ---- informational: GPU detection post-processing on the last frame's heads, outside the timed regions
+        post = None
+        if rank == 0 and not collective_path:
+            try:
+                import math
+                from heal_b200.data_utils.post_processor import build_postprocessor
+                rng = list(args["lidar_range"])
+                vs = args["m1"]["encoder_args"]["voxel_size"]
+                pcfg = {"core_method": "VoxelPostprocessor", "gt_range": rng, "order": "hwl", "nms_thresh": 0.15,
+                        "anchor_args": {"cav_lidar_range": rng, "l": 3.9, "w": 1.6, "h": 1.56, "r": [0, 90], "feature_stride": 2, "num": 2,
+                                        "vw": vs[0], "vh": vs[1], "W": math.ceil((rng[3] - rng[0]) / vs[0]),
+                                        "H": math.ceil((rng[4] - rng[1]) / vs[1])},
+                        "target_args": {"score_threshold": 0.2}, "dir_args": args["dir_args"]}
+                pp = build_postprocessor(pcfg, train=False)
+                out = frame_dev(0, eager=True)
+                cav = {"transformation_matrix": torch.eye(4), "anchor_box": torch.from_numpy(pp.generate_anchor_box())}
+                heads = {k: out[k] for k in ("cls_preds", "reg_preds", "dir_preds")}
+                buf = pp._decode_one(cav, heads)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    pp._decode_one(cav, heads)
+                b.record()
+                torch.cuda.synchronize()
+                st = buf.stats.cpu().tolist()
+                post = {"us_per_frame": a.elapsed_time(b) * 100.0, "above_threshold": st[0], "after_filters": st[1],
+                        "boxes_out": int(buf.count.item()),
+                        "note": "heal_box_decode_nms on the frame's heads (random-init weights: far more candidates than a trained model "
+                                "yields), device time, not part of `value` / `e2e`"}
+            except Exception as e:      # informational only
+                post = {"error": repr(e)[:200]}
+
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -463,6 +496,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "mode": ("FramePipeline: 2 captured frames, copy-in / compute / copy-out streams" if pipe is not None
                                  else "single stream: H2D -> frame -> D2H")},
+                "postprocess": post,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "gflop_per_frame": frame_flops(n_agents) / 1e9}
         print(json.dumps(line))
