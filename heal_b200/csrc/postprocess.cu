@@ -177,10 +177,16 @@ k_iou_mask(const double* __restrict__ poly, const int* __restrict__ counters, in
     double P[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) P[k] = poly[(size_t)i * 9 + k];
+    const double pminx = fmin(fmin(P[0], P[2]), fmin(P[4], P[6])), pmaxx = fmax(fmax(P[0], P[2]), fmax(P[4], P[6]));
+    const double pminy = fmin(fmin(P[1], P[3]), fmin(P[5], P[7])), pmaxy = fmax(fmax(P[1], P[3]), fmax(P[5], P[7]));
     unsigned long long bits = 0ull;
     for (int jj = 0; jj < cols; ++jj) {
         const int j = col0 + jj;
         if (j <= i) continue;
+        const double* Q = sq + jj * 9;
+        // disjoint bounding boxes: the clip would come back empty (IoU 0, or NaN for two zero-area boxes) -> never above the threshold
+        if (pmaxx < fmin(fmin(Q[0], Q[2]), fmin(Q[4], Q[6])) || fmax(fmax(Q[0], Q[2]), fmax(Q[4], Q[6])) < pminx ||
+            pmaxy < fmin(fmin(Q[1], Q[3]), fmin(Q[5], Q[7])) || fmax(fmax(Q[1], Q[3]), fmax(Q[5], Q[7])) < pminy) continue;
         const double inter = quad_intersection(P, sq + jj * 9);
         const double uni = P[8] + sq[jj * 9 + 8] - inter;
         const float iou = (float)(inter / uni);              // NaN for a zero-area union: never suppresses

@@ -22,6 +22,16 @@ _MAP = {
 }
 
 
+def install_gpu_postprocessor():
+    """Opt-in: make the reference's post-processor registry (opencood/data_utils/post_processor/__init__.py `__all__`) hand out the
+    GPU VoxelPostprocessor for inference of early / intermediate fusion (`generate_label` and late fusion's cross-cav NMS stay with
+    the reference class, so training and late-fusion configs must not call this)."""
+    from .data_utils.post_processor.voxel_postprocessor import VoxelPostprocessor
+    reg = importlib.import_module("opencood.data_utils.post_processor")
+    reg.__all__["VoxelPostprocessor"] = VoxelPostprocessor
+    return VoxelPostprocessor
+
+
 def install_into_opencood(only=None):
     """Alias the mirrors under their opencood module names (call BEFORE opencood.tools imports the models)."""
     done = []
