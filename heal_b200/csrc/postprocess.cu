@@ -103,7 +103,8 @@ k_decode(DecP p) {
 // top rows: [24 corner floats]; poly rows: 8 doubles (ccw x0 y0 .. x3 y3) + area
 __global__ void k_gather_top(const float* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, const float* __restrict__ cand,
                              const int* __restrict__ counters, int top, float* __restrict__ top_c, float* __restrict__ top_s,
-                             double* __restrict__ poly) {
+                             double* __restrict__ poly, float lx, float ly, float lz, float hx, float hy, float hz, int use_range,
+                             unsigned char* __restrict__ inrange) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(counters[1], top);
     if (r >= n) return;
@@ -112,6 +113,13 @@ __global__ void k_gather_top(const float* __restrict__ keys_sorted, const int* _
 #pragma unroll
     for (int k = 0; k < 24; ++k) { c[k] = src[k]; top_c[(size_t)r * 24 + k] = c[k]; }
     top_s[r] = keys_sorted[r];
+    bool in = true;                       // mask_boxes_outside_range_numpy: all 8 corners inside [min, max] on x, y and z
+    if (use_range) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            in = in && (c[3 * k] >= lx) && (c[3 * k] <= hx) && (c[3 * k + 1] >= ly) && (c[3 * k + 1] <= hy) && (c[3 * k + 2] >= lz) && (c[3 * k + 2] <= hz);
+    }
+    inrange[r] = in ? 1 : 0;
     double x[4], y[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { x[k] = (double)c[3 * k]; y[k] = (double)c[3 * k + 1]; }
@@ -195,15 +203,18 @@ k_iou_mask(const double* __restrict__ poly, const int* __restrict__ counters, in
     mask[(size_t)i * words + blockIdx.x] = bits;
 }
 
-// One block: all threads stage the suppression matrix (top x words x 8 B <= 128 KiB for top = 1000) in shared memory, then warp 0
-// does the greedy scan from there -- straight from global memory every kept box costs a dependent ~0.6 us load (0.5 ms per frame).
+// One block: all threads stage the suppression matrix (top x words x 8 B <= 128 KiB for top = 1000) and the in-range flags in shared
+// memory, then warp 0 does the greedy scan from there and lists the survivors that are also in range; k_emit copies them in
+// parallel.  (Reading the mask row and the corners of every kept box straight from global memory inside the scan costs two
+// dependent ~0.5 us loads per box: 0.5 ms per frame.)
 __global__ void __launch_bounds__(1024)
-k_nms_finish(const unsigned long long* __restrict__ mask, const int* __restrict__ counters, int top, int words,
-             const float* __restrict__ top_c, const float* __restrict__ top_s, float lx, float ly, float lz, float hx, float hy, float hz,
-             int use_range, float* __restrict__ boxes_out, float* __restrict__ scores_out, int* __restrict__ count_out) {
+k_nms_finish(const unsigned long long* __restrict__ mask, const unsigned char* __restrict__ inrange, const int* __restrict__ counters,
+             int top, int words, int* __restrict__ keep_idx, int* __restrict__ count_out) {
     extern __shared__ unsigned long long smask[];
     const int n = min(counters[1], top);
+    unsigned char* srange = reinterpret_cast<unsigned char*>(smask + (size_t)top * words);
     for (int k = threadIdx.x; k < n * words; k += blockDim.x) smask[k] = mask[k];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) srange[k] = inrange[k];
     __syncthreads();
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
@@ -213,21 +224,23 @@ k_nms_finish(const unsigned long long* __restrict__ mask, const int* __restrict_
         const int w = i >> 6;
         const unsigned long long mine = __shfl_sync(0xffffffffu, removed, w);
         if ((mine >> (i & 63)) & 1ull) continue;
-        // box i survives the NMS: suppress its overlaps, then apply the all-8-corners-in-range mask to decide whether it is output
+        // box i survives the NMS: it suppresses its overlaps whether or not it passes the range mask applied afterwards
         if (lane < words && lane >= w) removed |= smask[(size_t)i * words + lane];
-        const float* c = top_c + (size_t)i * 24;
-        bool in = true;
-        if (use_range && lane < 8) {
-            const float x = c[3 * lane], y = c[3 * lane + 1], z = c[3 * lane + 2];
-            in = (x >= lx) && (x <= hx) && (y >= ly) && (y <= hy) && (z >= lz) && (z <= hz);
-        }
-        if (__all_sync(0xffffffffu, in)) {
-            if (lane < 24) boxes_out[(size_t)kept * 24 + lane] = c[lane];
-            if (lane == 0) scores_out[kept] = top_s[i];
+        if (srange[i]) {
+            if (lane == 0) keep_idx[kept] = i;
             ++kept;
         }
     }
     if (lane == 0) *count_out = kept;
+}
+
+__global__ void k_emit(const int* __restrict__ keep_idx, const int* __restrict__ count, const float* __restrict__ top_c,
+                       const float* __restrict__ top_s, float* __restrict__ boxes_out, float* __restrict__ scores_out) {
+    const int r = blockIdx.x;
+    if (r >= *count) return;
+    const int i = keep_idx[r];
+    if (threadIdx.x < 24) boxes_out[(size_t)r * 24 + threadIdx.x] = top_c[(size_t)i * 24 + threadIdx.x];
+    if (threadIdx.x == 24) scores_out[r] = top_s[i];
 }
 
 inline ActV to_view(const heal_act_t* a) {
@@ -237,7 +250,7 @@ inline ActV to_view(const heal_act_t* a) {
 }
 
 struct WsLayout {
-    size_t keys_in, keys_out, vals_in, vals_out, cand, counters, top_c, top_s, poly, mask, cub, total, cub_bytes;
+    size_t keys_in, keys_out, vals_in, vals_out, cand, counters, top_c, top_s, poly, mask, inrange, keep, cub, total, cub_bytes;
     int words;
 };
 
@@ -256,6 +269,8 @@ WsLayout layout(int n, int top) {
     L.poly = o; o = al(o + (size_t)top * 9 * 8);
     L.words = (top + 63) / 64;
     L.mask = o; o = al(o + (size_t)top * L.words * 8);
+    L.inrange = o; o = al(o + (size_t)top);
+    L.keep = o; o = al(o + (size_t)top * 4);
     size_t cb = 0;
     cub::DeviceRadixSort::SortPairsDescending(nullptr, cb, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, n);
     L.cub_bytes = cb;
@@ -279,7 +294,7 @@ extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg,
     if (!cls || !cls->data || !reg || !reg->data || !anchors || !transform4x4_host || !boxes_out || !scores_out || !count_out || !workspace)
         return HEAL_ERR_ARG;
     if (cls->fmt != 0 || reg->fmt != 0 || (dir && dir->data && dir->fmt != 0)) return HEAL_ERR_UNSUPPORTED;
-    if (H < 1 || W < 1 || anchors_per_cell < 1 || top < 1 || top > 1344 || num_bins < 1) return HEAL_ERR_ARG;   // mask must fit 227 KiB of smem
+    if (H < 1 || W < 1 || anchors_per_cell < 1 || top < 1 || top > 1320 || num_bins < 1) return HEAL_ERR_ARG;   // mask must fit 227 KiB of smem
     const int n = H * W * anchors_per_cell;
     const WsLayout L = layout(n, top);
     if (workspace_bytes < L.total) return HEAL_ERR_ARG;
@@ -299,20 +314,23 @@ extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg,
     size_t cb = L.cub_bytes;
     if (cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cb, (const float*)p.keys, (float*)(ws + L.keys_out), (const int*)p.vals,
                                                   (int*)(ws + L.vals_out), n, 0, 32, st) != cudaSuccess) return HEAL_ERR_LAUNCH;
+    const float* r = range6_host;
+    const float rl[6] = {r ? r[0] : 0.f, r ? r[1] : 0.f, r ? r[2] : 0.f, r ? r[3] : 0.f, r ? r[4] : 0.f, r ? r[5] : 0.f};
     k_gather_top<<<(top + 127) / 128, 128, 0, st>>>((const float*)(ws + L.keys_out), (const int*)(ws + L.vals_out), p.cand, p.counters, top,
-                                                    (float*)(ws + L.top_c), (float*)(ws + L.top_s), (double*)(ws + L.poly));
+                                                    (float*)(ws + L.top_c), (float*)(ws + L.top_s), (double*)(ws + L.poly),
+                                                    rl[0], rl[1], rl[2], rl[3], rl[4], rl[5], r ? 1 : 0, (unsigned char*)(ws + L.inrange));
     dim3 g((top + 63) / 64, (top + 63) / 64);
     k_iou_mask<<<g, 64, 0, st>>>((const double*)(ws + L.poly), p.counters, top, nms_threshold, L.words, (unsigned long long*)(ws + L.mask));
-    const float* r = range6_host;
-    const size_t nms_smem = (size_t)top * L.words * 8;
+    const size_t nms_smem = (size_t)top * L.words * 8 + (((size_t)top + 15) & ~(size_t)15);
     static size_t nms_attr = 0;
     if (nms_smem > nms_attr) {
         if (cudaFuncSetAttribute(k_nms_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem) != cudaSuccess) return HEAL_ERR_LAUNCH;
         nms_attr = nms_smem;
     }
-    k_nms_finish<<<1, 1024, nms_smem, st>>>((const unsigned long long*)(ws + L.mask), p.counters, top, L.words, (const float*)(ws + L.top_c),
-                                   (const float*)(ws + L.top_s), r ? r[0] : 0.f, r ? r[1] : 0.f, r ? r[2] : 0.f, r ? r[3] : 0.f,
-                                   r ? r[4] : 0.f, r ? r[5] : 0.f, r ? 1 : 0, boxes_out, scores_out, count_out);
+    k_nms_finish<<<1, 1024, nms_smem, st>>>((const unsigned long long*)(ws + L.mask), (const unsigned char*)(ws + L.inrange), p.counters, top,
+                                            L.words, (int*)(ws + L.keep), count_out);
+    k_emit<<<top, 32, 0, st>>>((const int*)(ws + L.keep), count_out, (const float*)(ws + L.top_c), (const float*)(ws + L.top_s),
+                               boxes_out, scores_out);
     if (stats_out) cudaMemcpyAsync(stats_out, p.counters, 8, cudaMemcpyDeviceToDevice, st);
-    return heal_check_launch(4);
+    return heal_check_launch(5);
 }

@@ -212,7 +212,7 @@ int heal_sparse_to_bev(const float* feats, const int* coords, const int* rows_de
  *   transform4x4_host: row-major cav -> ego matrix; range6_host: [minx miny minz maxx maxy maxz] or NULL (no range mask)
  *   boxes_out (top,8,3) fp32, scores_out (top) fp32 in pick (score) order, count_out: device int = number of boxes written
  *   stats_out: device int[2] = anchors above the score threshold, after the size / z filters (NULL allowed)
- *   workspace >= heal_postprocess_workspace(H, W, A, top) bytes; top <= 1344 (the reference uses 1000) */
+ *   workspace >= heal_postprocess_workspace(H, W, A, top) bytes; top <= 1320 (the reference uses 1000) */
 size_t heal_postprocess_workspace(int H, int W, int anchors_per_cell, int top);
 int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal_act_t* dir, const float* anchors,
                         int H, int W, int anchors_per_cell, float score_threshold, float dir_offset, int num_bins,
