@@ -67,3 +67,21 @@ def test_training_mode_is_rejected_loudly():
     bb.train()
     with pytest.raises(NotImplementedError):
         bb({"spatial_features": torch.zeros(1, 64, 4, 4)})
+
+
+def test_postprocessor_anchor_box_equals_reference_golden(golden_dir):
+    """heal_b200's VoxelPostprocessor.generate_anchor_box (host logic) against the anchors the unmodified reference generated."""
+    import copy
+    import os
+    import numpy as np
+    import torch
+    from heal_b200.data_utils.post_processor import build_postprocessor
+    g = torch.load(os.path.join(golden_dir, "postprocess.pt"), weights_only=False)
+    pp = build_postprocessor(copy.deepcopy(g["params"]), train=False)
+    a = pp.generate_anchor_box()
+    assert a.dtype == np.float64 and np.array_equal(a, g["anchors"].numpy())
+    import pytest
+    with pytest.raises(NotImplementedError):
+        pp.generate_label()
+    with pytest.raises(NotImplementedError):      # late fusion: several cavs
+        pp.post_process({"a": {}, "b": {}}, {"a": {}, "b": {}})
