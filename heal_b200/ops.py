@@ -354,7 +354,7 @@ class PackedConvTC:
         self.kh, self.kw, self.pad, self.cin, self.cout, self.coutp = kh, kw, pad, cin, cout, coutp
         self.relu, self.up, self.planes = relu, up, planes
         self.stride, self.groups, self.blockdiag = stride, groups, blockdiag
-        self.w_diag = None       # grouped convs: [plane][tap][co][16] diagonal sub-blocks (weight-stationary halo path)
+        self.w_diag = None       # grouped convs: [plane][tap][co][16] diagonal sub-blocks (what the kernel streams)
 
     def to(self, device):
         self.w = self.w.to(device)

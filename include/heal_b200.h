@@ -115,9 +115,10 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
                      int upsample, int up_i, int up_j, int relu, void* stream);
 
 /* ---- 2-D convolution, tcgen05 tensor-core path ---------------------------------------------------
- * Same reference ops as heal_conv2d_nhwc_f32, evaluated as an implicit GEMM with tcgen05.mma (TMEM
+ * Same reference ops as heal_conv2d_simt, evaluated as an implicit GEMM with tcgen05.mma (TMEM
  * accumulators) fed by TMA.  Activations are "split-bf16": `planes` bf16 channels-last planes
- * (planes=2: hi = bf16(x), lo = bf16(x-hi), fp32-equivalent via 3 MMAs per K step; planes=1: plain bf16).
+ * (planes=2: hi = bf16(x), lo = bf16(x-hi), fp32-equivalent via the three products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi per K
+ * step; planes=1: plain bf16).
  *   in_split   bf16 [planes][N][H][W][in_cstride], plane stride in elements; Cin % 64 == 0
  *   w_packed   bf16 [planes][w_rows][Cin]; conv: w_rows = kh*kw*coutp, row = tap*coutp + co;
  *              transposed conv (kh=kw=1, upsample=k): w_rows = k*k*coutp, row = (i*k+j)*coutp + co;
@@ -129,7 +130,8 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
  *              64x64 channel blocks; w_packed is then [planes][kh*kw*coutp][64] (row = tap*coutp + co,
  *              column = input channel within co's 64-channel block, zeros outside co's group);
  *              w_diag (optional, NULL otherwise): the same weights as [planes][kh*kw][coutp][16] — only the 16x16 diagonal
- *              sub-block of each output channel — kept resident in shared memory when the conv runs with one-row tiles */
+ *              sub-block of each output channel; when given, the kernel streams these (a quarter of the bytes, 32 B-swizzled
+ *              TMA boxes) instead of the 64-wide rows of w_packed */
 int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
                    const void* w_packed, const void* w_diag, int w_rows, int coutp, const float* bias,
                    int kh, int kw, int stride, int pad, int blockdiag, int planes,
