@@ -76,13 +76,38 @@ def frame_flops(n_agents=N_AGENTS, H=256, W=256):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed regions.  NVML is polled every ~5 ms from a thread (a 20-step region lasts
+    ~70 ms); `nvidia-smi -lms 100` runs next to it as the fallback when NVML is unavailable or returned too few samples."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nv, self.nv_max, self.nv_reasons, self._stop = [], None, set(), False
+
+    def _poll_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+            while not self._stop:
+                self.nv.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    m = int(get_reasons(h))
+                    for name, bit in self.BITS:
+                        if m & bit:
+                            self.nv_reasons.add(name)
+                time.sleep(0.005)
+        except Exception:
+            pass
 
     def start(self):
+        threading.Thread(target=self._poll_nvml, daemon=True).start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -96,10 +121,10 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        self._stop = True
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm, mx, reasons = [], None, set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -112,8 +137,13 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if len(self.nv) >= 5:
+            return {"sm_mhz": float(np.median(self.nv)), "sm_min_mhz": float(min(self.nv)), "sm_max_mhz": self.nv_max or mx,
+                    "reasons": sorted(self.nv_reasons | reasons), "samples": len(self.nv), "source": "nvml @5ms (+ nvidia-smi -lms 100)"}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def build_scenes(n_scenes, n_agents, seed0=100):
