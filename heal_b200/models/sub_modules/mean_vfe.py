@@ -1,4 +1,8 @@
-"""MeanVFE mirror (opencood/models/sub_modules/mean_vfe.py:13-33) on heal_mean_vfe."""
+"""MeanVFE (reference: opencood/models/sub_modules/mean_vfe.py:13-33): per-voxel mean of the point slots, the VFE of the SECOND encoder.
+
+One launch of `heal_mean_vfe` (csrc/voxelize.cu): thread per (voxel, feature), sum over the T zero-padded slots divided by
+max(num_points, 1) in the reference's order of operations; parameter-free, so there is no state dict to mirror -- only the
+constructor signature, `get_output_feature_dim` and the batch_dict keys ('voxel_features' in: (M, T, C); out: (M, C))."""
 import torch.nn as nn
 
 from ... import ops
