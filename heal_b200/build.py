@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"[heal_b200.build] {src}\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(dig)
