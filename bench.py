@@ -398,6 +398,22 @@ def main():
         barrier()
         e2e_ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
+        # the same steps without any overlap (one stream: H2D -> frame -> D2H back to back), reported next to the pipelined figure
+        e2e_serial = None
+        if pipe is not None and rank == 0:
+            try:
+                for w in range(2):
+                    frame_e2e(w)
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for k in range(opt.steps):
+                    frame_e2e(k)
+                s1.record()
+                torch.cuda.synchronize()
+                e2e_serial = opt.steps / (s0.elapsed_time(s1) / 1e3)
+            except Exception:
+                e2e_serial = None
 
         # ---- instrumented pass: per-kernel-family device time (events around every C-ABI conv call) ----
         prof = None
@@ -544,7 +560,8 @@ def main():
                                           else "agent-per-GPU + 1 NCCL all-gather", opt.precision),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "mode": ("FramePipeline: 2 captured frames, copy-in / compute / copy-out streams" if pipe is not None
-                                 else "single stream: H2D -> frame -> D2H")},
+                                 else "single stream: H2D -> frame -> D2H"),
+                        "single_stream_value_rank0": e2e_serial},
                 "postprocess": post,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "gflop_per_frame": frame_flops(n_agents) / 1e9}
