@@ -26,6 +26,7 @@ SIGNATURES = {
     "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _ap, _vp]),
+    "heal_pillar_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ap, _vp]),
     "heal_pillar_idmap": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "heal_sparse_stem": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _ap, _ap, _vp]),
     "heal_sparse_stem_tc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _ap, _ap, _vp]),
@@ -33,7 +34,7 @@ SIGNATURES = {
                               _i, _i, _i, _i, _vp]),
     "heal_conv2d_tc": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i,
                             _vp, _sz, _vp, _i, _i, _vp, _sz, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "heal_pyramid_fuse_level": (_i, [_ap, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ap, _vp]),
+    "heal_pyramid_fuse_level": (_i, [_ap, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _ap, _vp]),
     "heal_att_fuse": (_i, [_ap, _vp, _i, _i, _i, _i, _ap, _vp]),
     "heal_act_convert": (_i, [_ap, _ap, _sz, _i, _vp]),
     "heal_postprocess_workspace": (_sz, [_i, _i, _i, _i]),

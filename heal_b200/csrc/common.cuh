@@ -23,6 +23,20 @@ static inline int heal_check_launch(int kernels_launched = 1) {
     return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember the largest value set per device ordinal
+// (a process that drives several GPUs must set it on each of them).
+#define HEAL_MAX_DEVICES 64
+template <typename K>
+static inline bool heal_ensure_dyn_smem(K kernel, size_t bytes, size_t (&set_for_device)[HEAL_MAX_DEVICES]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const bool tracked = dev >= 0 && dev < HEAL_MAX_DEVICES;
+    if (tracked && set_for_device[dev] >= bytes) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    if (tracked) set_for_device[dev] = bytes;
+    return true;
+}
+
 static inline size_t heal_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over a caller-provided workspace; no internal allocation anywhere in the library.

@@ -671,6 +671,17 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
+// HEAL_TC_* measurement hooks (profiles/tc_experiment.py), read once per process instead of six getenv calls per launch.
+struct TcEnv {
+    int dbg, pdl, halo, bo, tma_store, res_tma;
+    TcEnv() {
+        auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
+        dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 0); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
+        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1);
+    }
+};
+const TcEnv& tc_env() { static const TcEnv e; return e; }
+
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -695,12 +706,8 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * b_tile;
     size_t smem = (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_conv2d_tc<BLOCK_N, STAGES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return HEAL_ERR_LAUNCH;
-        attr_set = true;
-    }
+    static size_t attr_set[HEAL_MAX_DEVICES] = {};
+    if (!heal_ensure_dyn_smem(k_conv2d_tc<BLOCK_N, STAGES, STG>, 227 * 1024, attr_set)) return HEAL_ERR_LAUNCH;
     int total = p.m_tiles * p.n_tiles;
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
     if (grid < 1) return HEAL_ERR_UNSUPPORTED;
@@ -754,17 +761,16 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     p.stride = stride; p.blockdiag = blockdiag;
     if (upsample > 1) p.n_tiles = w_rows / block_n;
     p.planes = planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
-    { const char* e = getenv("HEAL_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
-    { const char* e = getenv("HEAL_TC_PDL"); p.pdl = e ? atoi(e) : 0; }
+    const TcEnv& env = tc_env();
+    p.dbg = env.dbg; p.pdl = env.pdl;
     p.res_split = (const __nv_bfloat16*)res_split; p.res_plane = res_plane_stride; p.res_f32 = res_f32;
     p.res_cs = res_cstride; p.res_co = res_coffset;
     p.out_split = (__nv_bfloat16*)out_split; p.out_plane = out_plane_stride; p.out_cs = out_cstride; p.out_co = out_coffset;
     p.out_f32 = out_f32; p.out32_cs = out32_cstride; p.out32_co = out32_coffset;
 
     {
-        const char* e = getenv("HEAL_TC_HALO");
-        const bool want = !(e && atoi(e) == 0);
-        { const char* b = getenv("HEAL_TC_BO"); p.bo_mode = b ? atoi(b) : 0; }
+        const bool want = env.halo != 0;
+        p.bo_mode = env.bo;
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
     }
     CUtensorMap tmA, tmB;
@@ -837,8 +843,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     CUtensorMap tmO = tmA;
     p.tma_out = 0;
     {
-        const char* e = getenv("HEAL_TC_TMA_STORE");
-        const bool want = !(e && atoi(e) == 0);
+        const bool want = env.tma_store != 0;
         if (want && out_split && upsample == 1 && block_n >= 64 && (Cout % 64) == 0 && !(out_cstride & 7) && !(out_coffset & 7) &&
             (!res_split || (!(res_cstride & 7) && !(res_coffset & 7)))) {
             cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N, (cuuint64_t)planes};
@@ -858,8 +863,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     CUtensorMap tmR = tmO;
     bool res_tma_ok = false;
     {
-        const char* e = getenv("HEAL_TC_RES_TMA");
-        const bool want = !(e && atoi(e) == 0);
+        const bool want = env.res_tma != 0;
         if (want && p.tma_out && res_split) {
             cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N, (cuuint64_t)planes};
             cuuint64_t strides[4] = {(cuuint64_t)res_cstride * 2, (cuuint64_t)Wo * res_cstride * 2, (cuuint64_t)Ho * Wo * res_cstride * 2,

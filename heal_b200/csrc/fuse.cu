@@ -54,9 +54,18 @@ struct FuseP {
     const float* occ;      // (n, H, W) occupancy logits
     const double* theta;   // (n, 2, 3) fp64: affine[b, 0, j]
     const int* crop;       // (n, 4) [h0, h1, w0, w1] window where the score is kept, or nullptr
-    ActV out;              // (H, W, C)
+    ActV out;              // (rows, W, C): the output slab, pixel 0 = (row0, 0)
     int n, H, W, C, align;
+    int row0, rows;        // output rows [row0, row0 + rows) (row-sharded fusion tail); whole map: 0, H
+    long long foff[MAX_AGENTS];   // element offset of agent j's map from feat.p (dense stack: j*H*W*cstride; gathered buffer: any)
+    long long ooff[MAX_AGENTS];   // element offset of agent j's occupancy map from occ
 };
+
+__device__ __forceinline__ ActV agent_view(const ActV& f, long long off) {
+    ActV v = f;
+    v.p = (f.fmt == 0) ? (void*)(reinterpret_cast<float*>(f.p) + off) : (void*)(reinterpret_cast<__nv_bfloat16*>(f.p) + off);
+    return v;
+}
 
 // FUSE_PIX pixels per 256-thread block, chosen by the host so that FUSE_PIX * C / 4 == 256 (one 4-channel chunk per thread)
 // and small maps still fill the machine (64x64x256 -> 1024 blocks).
@@ -65,15 +74,15 @@ __global__ void __launch_bounds__(256)
 k_pyramid_fuse(FuseP p) {
     __shared__ Tap sTap[FUSE_PIX][MAX_AGENTS];
     __shared__ float sScore[FUSE_PIX][MAX_AGENTS];
-    const int HW = p.H * p.W;
+    const int HW = p.rows * p.W;                   // pixels of the output slab; `pix` below is slab-local
     const int pix0 = blockIdx.x * FUSE_PIX;
     // phase 1: tap geometry + warped score per (pixel, agent)
     for (int it = threadIdx.x; it < FUSE_PIX * p.n; it += blockDim.x) {
         int j = it % p.n, lp = it / p.n;
         int pix = pix0 + lp;
         if (pix >= HW) continue;
-        Tap t = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
-        const float* occ = p.occ + (size_t)j * HW;
+        Tap t = make_tap(p.theta + 6 * j, p.row0 + pix / p.W, pix % p.W, p.H, p.W, p.align);
+        const float* occ = p.occ + p.ooff[j];
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -126,7 +135,7 @@ k_pyramid_fuse(FuseP p) {
                 int off = sTap[lp][j].off[k];
                 w[k] = sTap[lp][j].w[k];
                 v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (off >= 0) v[k] = act_load4(p.feat, (size_t)j * HW + off, ch * 4);
+                if (off >= 0) v[k] = act_load4(agent_view(p.feat, p.foff[j]), (size_t)off, ch * 4);
                 else w[k] = 0.f;
             }
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,14 +158,14 @@ __global__ void __launch_bounds__(256)
 k_pyramid_fuse_split8(FuseP p) {
     __shared__ Tap sTap[FUSE_PIX][MAX_AGENTS];
     __shared__ float sScore[FUSE_PIX][MAX_AGENTS];
-    const int HW = p.H * p.W;
+    const int HW = p.rows * p.W;
     const int pix0 = blockIdx.x * FUSE_PIX;
     for (int it = threadIdx.x; it < FUSE_PIX * p.n; it += blockDim.x) {
         int j = it % p.n, lp = it / p.n;
         int pix = pix0 + lp;
         if (pix >= HW) continue;
-        Tap t = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
-        const float* occ = p.occ + (size_t)j * HW;
+        Tap t = make_tap(p.theta + 6 * j, p.row0 + pix / p.W, pix % p.W, p.H, p.W, p.align);
+        const float* occ = p.occ + p.ooff[j];
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -168,7 +177,7 @@ k_pyramid_fuse_split8(FuseP p) {
                     if (!(y >= c[0] && y < c[1] && x >= c[2] && x < c[3])) sc = 0.f;
                 }
                 s += sc * t.w[k];
-                t.off[k] = (j * HW + t.off[k]) * p.feat.cs + p.feat.co;      // element index of the tap's first channel
+                t.off[k] = t.off[k] * p.feat.cs + p.feat.co;      // element index of the tap's first channel inside agent j's map
             }
         }
         sTap[lp][j] = t;
@@ -204,6 +213,8 @@ k_pyramid_fuse_split8(FuseP p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         for (int j = 0; j < p.n; ++j) {
+            const __nv_bfloat16* hj = hi + p.foff[j];
+            const __nv_bfloat16* lj = lo + p.foff[j];
             uint4 vh[4], vl[4];
             float w[4];
 #pragma unroll
@@ -212,8 +223,8 @@ k_pyramid_fuse_split8(FuseP p) {
                 w[k] = sTap[lp][j].w[k];
                 vh[k] = make_uint4(0u, 0u, 0u, 0u); vl[k] = make_uint4(0u, 0u, 0u, 0u);
                 if (off >= 0) {
-                    vh[k] = __ldg(reinterpret_cast<const uint4*>(hi + off + ch * 8));
-                    vl[k] = __ldg(reinterpret_cast<const uint4*>(lo + off + ch * 8));
+                    vh[k] = __ldg(reinterpret_cast<const uint4*>(hj + off + ch * 8));
+                    vl[k] = __ldg(reinterpret_cast<const uint4*>(lj + off + ch * 8));
                 } else {
                     w[k] = 0.f;
                 }
@@ -321,18 +332,29 @@ static inline ActV to_view(const heal_act_t* a) {
 
 extern "C" int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ, const double* theta,
                                        const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
-                                       const heal_act_t* out, void* stream_) {
+                                       const long long* agent_feat_offsets_host, const long long* agent_occ_offsets_host,
+                                       int row0, int rows, const heal_act_t* out, void* stream_) {
     if (!feat || !feat->data || !occ || !theta || !out || !out->data) return HEAL_ERR_ARG;
     if (n_agents < 1 || n_agents > MAX_AGENTS) return HEAL_ERR_UNSUPPORTED;
+    if (rows <= 0) { row0 = 0; rows = H; }
+    if (row0 < 0 || row0 + rows > H) return HEAL_ERR_ARG;
     if ((C & 3) || (feat->cstride & 3) || (feat->coffset & 3) || (out->cstride & 3) || (out->coffset & 3)) return HEAL_ERR_UNSUPPORTED;
     FuseP p;
     p.feat = to_view(feat); p.occ = occ; p.theta = theta; p.crop = crop_windows; p.out = to_view(out);
     p.n = n_agents; p.H = H; p.W = W; p.C = C; p.align = align_corners;
+    p.row0 = row0; p.rows = rows;
+    bool off8 = true;
+    for (int j = 0; j < MAX_AGENTS; ++j) {
+        p.foff[j] = (j < n_agents) ? (agent_feat_offsets_host ? agent_feat_offsets_host[j] : (long long)j * H * W * feat->cstride) : 0;
+        p.ooff[j] = (j < n_agents) ? (agent_occ_offsets_host ? agent_occ_offsets_host[j] : (long long)j * H * W) : 0;
+        if (p.foff[j] & 7) off8 = false;
+        if (p.foff[j] & 3) return HEAL_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream_;
-    const int HW = H * W;
-    // split-bf16 input, 16 B-aligned channel groups, element indices that fit 31 bits: the 8-channel kernel
-    if (feat->fmt == 2 && (C & 7) == 0 && (feat->cstride & 7) == 0 && (feat->coffset & 7) == 0 && (feat->plane_stride & 7) == 0 &&
-        (long long)n_agents * HW * feat->cstride < (1LL << 31)) {
+    const int HW = rows * W;
+    // split-bf16 input, 16 B-aligned channel groups, per-agent element indices that fit 31 bits: the 8-channel kernel
+    if (feat->fmt == 2 && (C & 7) == 0 && (feat->cstride & 7) == 0 && (feat->coffset & 7) == 0 && (feat->plane_stride & 7) == 0 && off8 &&
+        (long long)H * W * feat->cstride < (1LL << 31)) {
         if (C >= 256)      k_pyramid_fuse_split8<8><<<(HW + 7) / 8, 256, 0, st>>>(p);
         else if (C >= 128) k_pyramid_fuse_split8<16><<<(HW + 15) / 16, 256, 0, st>>>(p);
         else               k_pyramid_fuse_split8<32><<<(HW + 31) / 32, 256, 0, st>>>(p);

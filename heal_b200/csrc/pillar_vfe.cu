@@ -42,7 +42,9 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     int n = num_points[v];
     int4 cd = coords[v];  // [b, z, y, x]
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < c.T) p = __ldg(voxels + (size_t)v * c.T + lane);
+    // only the n real slots are read: the padded ones are zero by contract (sp_voxel_preprocessor zero-fills) and would add +0
+    // to the three sums, so skipping them is bit-identical and saves (T - n) * 16 B of DRAM reads per pillar (~10x on LiDAR pillars)
+    if (lane < min(n, c.T)) p = __ldg(voxels + (size_t)v * c.T + lane);
     float fn = (float)n;
     float mx = __fdiv_rn(warp_sum(p.x), fn), my = __fdiv_rn(warp_sum(p.y), fn), mz = __fdiv_rn(warp_sum(p.z), fn);
     float cx = __fadd_rn(__fmul_rn((float)cd.w, c.vx), c.xoff);
@@ -93,7 +95,32 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     }
 }
 
+// Stand-alone PointPillarScatter (point_pillar_scatter.py:19-77): rows of already computed pillar features -> canvas cells.
+// One warp per pillar, lanes over channel pairs; the caller pre-zeroes the canvas.
+__global__ void __launch_bounds__(256)
+k_pillar_scatter(const float* __restrict__ feats, const int4* __restrict__ coords, const int* __restrict__ num_voxels_dev, int M,
+                 int C, int nx, int ny, ActV canvas) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + warp;
+    const int Mdev = num_voxels_dev ? min(M, num_voxels_dev[0]) : M;
+    if (v >= Mdev) return;
+    const int4 cd = coords[v];
+    const size_t cell = ((size_t)cd.x * ny + (size_t)cd.z) * nx + (size_t)(cd.y + cd.w);
+    for (int c = lane; c < C; c += 32) act_store1(canvas, cell, c, __ldg(feats + (size_t)v * C + c));
+}
+
 }  // namespace
+
+extern "C" int heal_pillar_scatter(const float* pillar_features, const int* voxel_coords, const int* num_voxels_dev, int num_voxels,
+                                   int channels, int nx, int ny, const heal_act_t* canvas_out, void* stream_) {
+    if (!pillar_features || !voxel_coords || !canvas_out || !canvas_out->data || channels < 1) return HEAL_ERR_ARG;
+    if (num_voxels <= 0) return HEAL_OK;
+    ActV cv;
+    cv.p = canvas_out->data; cv.fmt = canvas_out->fmt; cv.cs = canvas_out->cstride; cv.co = canvas_out->coffset; cv.plane = canvas_out->plane_stride;
+    k_pillar_scatter<<<(num_voxels + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(pillar_features, (const int4*)voxel_coords, num_voxels_dev,
+                                                                            num_voxels, channels, nx, ny, cv);
+    return heal_check_launch();
+}
 
 extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_points, const int* voxel_coords,
                                        const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,

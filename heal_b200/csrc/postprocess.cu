@@ -322,11 +322,8 @@ extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg,
     dim3 g((top + 63) / 64, (top + 63) / 64);
     k_iou_mask<<<g, 64, 0, st>>>((const double*)(ws + L.poly), p.counters, top, nms_threshold, L.words, (unsigned long long*)(ws + L.mask));
     const size_t nms_smem = (size_t)top * L.words * 8 + (((size_t)top + 15) & ~(size_t)15);
-    static size_t nms_attr = 0;
-    if (nms_smem > nms_attr) {
-        if (cudaFuncSetAttribute(k_nms_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem) != cudaSuccess) return HEAL_ERR_LAUNCH;
-        nms_attr = nms_smem;
-    }
+    static size_t nms_attr[HEAL_MAX_DEVICES] = {};
+    if (!heal_ensure_dyn_smem(k_nms_finish, nms_smem, nms_attr)) return HEAL_ERR_LAUNCH;
     k_nms_finish<<<1, 1024, nms_smem, st>>>((const unsigned long long*)(ws + L.mask), (const unsigned char*)(ws + L.inrange), p.counters, top,
                                             L.words, (int*)(ws + L.keep), count_out);
     k_emit<<<top, 32, 0, st>>>((const int*)(ws + L.keep), count_out, (const float*)(ws + L.top_c), (const float*)(ws + L.top_s),

@@ -247,11 +247,8 @@ extern "C" int heal_sparse_stem_tc(const float* pillar_features, const int* idma
     p.out1.p = out_conv->data; p.out1.fmt = out_conv->fmt; p.out1.cs = out_conv->cstride; p.out1.co = out_conv->coffset; p.out1.plane = out_conv->plane_stride;
     p.out2.p = out_down->data; p.out2.fmt = out_down->fmt; p.out2.cs = out_down->cstride; p.out2.co = out_down->coffset; p.out2.plane = out_down->plane_stride;
     p.B = batch; p.ny = ny; p.nx = nx; p.Ho = ny / 2; p.Wo = nx / 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_sparse_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM) != cudaSuccess) return HEAL_ERR_LAUNCH;
-        attr_set = true;
-    }
+    static size_t attr_set[HEAL_MAX_DEVICES] = {};
+    if (!heal_ensure_dyn_smem(k_sparse_stem_tc, ST_SMEM, attr_set)) return HEAL_ERR_LAUNCH;
     long long ngroups = (long long)batch * p.Ho * (p.Wo / 16);
     long long blocks = (ngroups + 7) / 8;
     k_sparse_stem_tc<<<(unsigned)(blocks < HEAL_NUM_SMS ? blocks : HEAL_NUM_SMS), 256, ST_SMEM, (cudaStream_t)stream_>>>(p);

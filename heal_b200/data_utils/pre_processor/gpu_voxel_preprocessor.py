@@ -35,5 +35,7 @@ class GpuVoxelPreprocessor:
             sys.exit('Batch has too be a list or a dictionarn')
         offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
         pts = np.concatenate(clouds) if len(clouds) else np.zeros((0, 4), np.float32)
+        # the yaml's voxelisation limits travel with the batch: the encoders use them instead of their defaults
         return {'points': torch.from_numpy(pts), 'agent_offsets': torch.from_numpy(offs),
-                'agent_offsets_host': offs.tolist()}
+                'agent_offsets_host': offs.tolist(),
+                'max_points_per_voxel': int(self.max_points_per_voxel), 'max_voxels': int(self.max_voxels)}

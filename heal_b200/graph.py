@@ -12,6 +12,48 @@ import torch
 from ._lib import lib
 
 
+class GraphedCall:
+    """Generic capture: `fn(build(buffers))` over named static input buffers.  `spec` maps a name to (shape, dtype);
+    names in `varlen` may be loaded with fewer rows than their capacity (prefix copy; the live length travels in another input,
+    e.g. `agent_offsets[-1]`).  Used by bench.py for the single-agent / SECOND / camera workloads."""
+
+    def __init__(self, fn, spec, build, device, varlen=(), init=None, warmup=2):
+        self.bufs = {k: torch.zeros(tuple(shape), dtype=dt, device=device) for k, (shape, dt) in spec.items()}
+        self.varlen = set(varlen)
+        if init is not None:
+            self.load(**init)
+        self.data = build(self.bufs)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                fn(self.data)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = lib.heal_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = fn(self.data)
+        self.kernels_per_replay = int(lib.heal_launch_count() - l0)
+
+    def load(self, **tensors):
+        nbytes = 0
+        for k, t in tensors.items():
+            b = self.bufs[k]
+            if k in self.varlen:
+                if t.shape[0] > b.shape[0]:
+                    raise ValueError(f"{k}: {t.shape[0]} rows, graph capacity is {b.shape[0]}")
+                b[:t.shape[0]].copy_(t, non_blocking=True)
+            else:
+                b.copy_(t, non_blocking=True)
+            nbytes += t.numel() * t.element_size()
+        return nbytes
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 class FrameGraph:
     def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, modality: str = "m1", forward_fn=None,
                  device=None, warmup: int = 2):

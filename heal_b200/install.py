@@ -23,13 +23,16 @@ _MAP = {
 
 
 def install_gpu_postprocessor():
-    """Opt-in: make the reference's post-processor registry (opencood/data_utils/post_processor/__init__.py `__all__`) hand out the
-    GPU VoxelPostprocessor for inference of early / intermediate fusion (`generate_label` and late fusion's cross-cav NMS stay with
-    the reference class, so training and late-fusion configs must not call this)."""
-    from .data_utils.post_processor.voxel_postprocessor import VoxelPostprocessor
+    """Opt-in: make the reference's post-processor registry (opencood/data_utils/post_processor/__init__.py `__all__`) hand out a
+    SUBCLASS of its own VoxelPostprocessor whose `post_process` runs on the GPU for early / intermediate fusion and falls back to
+    the reference implementation for everything else (late fusion, iou_preds, CPU tensors).  All label / collate / gt-box methods
+    the datasets call are inherited unchanged."""
+    from .data_utils.post_processor.voxel_postprocessor import make_reference_subclass
     reg = importlib.import_module("opencood.data_utils.post_processor")
-    reg.__all__["VoxelPostprocessor"] = VoxelPostprocessor
-    return VoxelPostprocessor
+    ref_cls = importlib.import_module("opencood.data_utils.post_processor.voxel_postprocessor").VoxelPostprocessor
+    cls = make_reference_subclass(ref_cls)
+    reg.__all__["VoxelPostprocessor"] = cls
+    return cls
 
 
 def install_into_opencood(only=None):

@@ -47,8 +47,8 @@ class PyramidFusion(ResNetBEVBackbone):
         for i in range(self.num_levels):
             setattr(self, f"single_head_{i}", nn.Conv2d(model_cfg["num_filters"][i], 1, kernel_size=1))
 
-    def _occ_nhwc(self, feat, i):
-        return conv_bn_act(feat, getattr(self, f"single_head_{i}"), None, relu=False, out_fmt="f32")   # Act f32 (N,H,W,1)
+    def _occ_nhwc(self, feat, i, out=None):
+        return conv_bn_act(feat, getattr(self, f"single_head_{i}"), None, relu=False, out=out, out_fmt="f32")   # Act f32 (N,H,W,1)
 
     def forward_single(self, spatial_features):
         require_eval(self)

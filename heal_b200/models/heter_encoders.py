@@ -48,8 +48,8 @@ class PointPillar(nn.Module):
         else:
             pts, offs = inp['points'], inp['agent_offsets']
             vf, vc, vn, nvox_dev = ops.voxelize(pts, offs, self.lidar_range, self.voxel_size,
-                                                self.voxelize_args['max_points_per_voxel'],
-                                                self.voxelize_args['max_voxels'])
+                                                int(inp.get('max_points_per_voxel', self.voxelize_args['max_points_per_voxel'])),
+                                                int(inp.get('max_voxels', self.voxelize_args['max_voxels'])))
             batch_size = offs.numel() - 1
         w, b = self.pillar_vfe.folded()
         if sparse:
@@ -202,7 +202,8 @@ class SECOND(nn.Module):
                 batch_size = int(vc[:, 0].max().item()) + 1          # host sync, as the reference (heter_encoders.py:70)
         else:
             vf, vc, vn, nvox = ops.voxelize(inp['points'], inp['agent_offsets'], self.lidar_range, self.voxel_size,
-                                            self.voxelize_args['max_points_per_voxel'], self.voxelize_args['max_voxels'])
+                                            int(inp.get('max_points_per_voxel', self.voxelize_args['max_points_per_voxel'])),
+                                            int(inp.get('max_voxels', self.voxelize_args['max_voxels'])))
             rows_dev = nvox[0:1]
             batch_size = inp['agent_offsets'].numel() - 1
         feats = ops.mean_vfe(vf.contiguous(), vn)

@@ -23,7 +23,8 @@ class FusedHeads:
         self._conv = None
         self._sig = None
 
-    def __call__(self, x_nhwc):
+    def prepare(self):
+        """(Re)build the concatenated 1x1 conv when a head's parameters changed."""
         from ..engine import _sig
         sig = _sig(*self.heads)
         if self._conv is None or self._sig != sig:
@@ -34,6 +35,9 @@ class FusedHeads:
                 conv.weight.copy_(torch.cat([h.weight for h in self.heads], 0))
                 conv.bias.copy_(torch.cat([h.bias for h in self.heads], 0))
             self._conv, self._sig = conv, sig
+
+    def __call__(self, x_nhwc):
+        self.prepare()
         y = conv_bn_act(x_nhwc, self._conv, None, relu=False, out_fmt="f32").t          # (B,H,W,sum) fp32
         outs, o = [], 0
         for h in self.heads:

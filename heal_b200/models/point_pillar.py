@@ -26,6 +26,7 @@ class PointPillar(nn.Module):
         is_resnet = args['base_bev_backbone'].get("resnet", False)
         self.backbone = ResNetBEVBackbone(args['base_bev_backbone'], 64) if is_resnet else BaseBEVBackbone(args['base_bev_backbone'], 64)
         self.voxel_size, self.lidar_range = [float(v) for v in args['voxel_size']], [float(v) for v in args['lidar_range']]
+        self.voxelize_args = args.get('voxelize', {'max_points_per_voxel': 32, 'max_voxels': 70000})
         self.shrink_flag = 'shrink_header' in args
         if self.shrink_flag:
             self.shrink_conv = DownsampleConv(args['shrink_header'])
@@ -44,12 +45,23 @@ class PointPillar(nn.Module):
     def forward(self, data_dict):
         require_eval(self)
         inp = data_dict['processed_lidar']
-        vc = inp['voxel_coords']
-        batch_size = int(vc[:, 0].max().item()) + 1
+        nvox_dev = None
+        if 'voxel_features' in inp:
+            vf, vc, vn = inp['voxel_features'], inp['voxel_coords'], inp['voxel_num_points']
+            batch_size = inp.get('batch_size')
+            if batch_size is None:
+                batch_size = int(vc[:, 0].max().item()) + 1     # host sync, as the reference (point_pillar_scatter.py:45)
+        else:
+            # raw points (`points`, `agent_offsets`): GPU voxelisation, no host sync (graph-capturable frame)
+            va = self.voxelize_args
+            vf, vc, vn, nvox_dev = ops.voxelize(inp['points'], inp['agent_offsets'], self.lidar_range, self.voxel_size,
+                                                int(inp.get('max_points_per_voxel', va['max_points_per_voxel'])),
+                                                int(inp.get('max_voxels', va['max_voxels'])))
+            batch_size = inp['agent_offsets'].numel() - 1
         w, b = self.pillar_vfe.folded()
-        _, canvas = ops.pillar_vfe_scatter(inp['voxel_features'], inp['voxel_num_points'], vc, w, b, self.voxel_size,
+        _, canvas = ops.pillar_vfe_scatter(vf, vn, vc, w, b, self.voxel_size,
                                            self.lidar_range, nx=self.scatter.nx, ny=self.scatter.ny, batch_size=batch_size,
-                                           canvas_fmt=act_fmt())
+                                           num_voxels_dev=nvox_dev, canvas_fmt=act_fmt())
         x = self.backbone.decode_nhwc(self.backbone.multiscale_nhwc(canvas))
         if self.shrink_flag:
             x = self.shrink_conv.forward_nhwc(x)

@@ -62,8 +62,8 @@ class ResNetBEVBackbone(nn.Module):
         self.num_bev_features = c_in
 
     # ---- channels-last internals (Act in / Act out) ---------------------------------------------
-    def multiscale_nhwc(self, x):
-        return self.resnet.forward_nhwc(x)
+    def multiscale_nhwc(self, x, outs=None):
+        return self.resnet.forward_nhwc(x, outs=outs)
 
     def decode_nhwc(self, feats):
         return decode_levels(self.deblocks, feats)

@@ -5,6 +5,8 @@ encoders never materialises them).  Output is logically (B, C, ny, nx), physical
 import torch
 import torch.nn as nn
 
+from ... import ops
+
 
 class PointPillarScatter(nn.Module):
     def __init__(self, model_cfg):
@@ -21,9 +23,6 @@ class PointPillarScatter(nn.Module):
         if pf.dim() == 1:
             pf = pf.unsqueeze(0)
         batch_size = int(coords[:, 0].max().item()) + 1      # same host sync as the reference (:45)
-        canvas = torch.zeros((batch_size * self.ny * self.nx, self.num_bev_features), dtype=pf.dtype, device=pf.device)
-        c = coords.long()
-        idx = c[:, 0] * (self.ny * self.nx) + c[:, 1] + c[:, 2] * self.nx + c[:, 3]
-        canvas.index_copy_(0, idx, pf)   # row scatter of a channels-last canvas (plumbing; fused path = heal_pillar_vfe_scatter)
-        batch_dict['spatial_features'] = canvas.view(batch_size, self.ny, self.nx, -1).permute(0, 3, 1, 2)
+        canvas = ops.pillar_scatter(pf.float().contiguous(), coords, self.nx, self.ny, batch_size)      # heal_pillar_scatter
+        batch_dict['spatial_features'] = ops.act_to_nchw(canvas)
         return batch_dict

@@ -121,28 +121,30 @@ class ResNetModified(nn.Module):
     # 7.4 ms/frame agent-major vs 5.9 ms batched, profiles/); set HEAL_AGENT_MAJOR_MB to experiment.
     AGENT_MAJOR_BYTES = (int(__import__('os').environ.get('HEAL_AGENT_MAJOR_MB', '0')) << 20) or (1 << 62)
 
-    def _run_level(self, layer, x):
+    def _run_level(self, layer, x, out=None):
         blocks = list(layer)
         stride = blocks[0].stride
         Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
         widest = max(max(getattr(b, "conv1").out_channels, b.out_channels) for b in blocks)
         biggest = x.N * max(x.H * x.W * max(x.C, blocks[0].conv1.out_channels), Ho * Wo * widest) * 4
         if x.N == 1 or biggest <= self.AGENT_MAJOR_BYTES or isinstance(x, ops.SparseCanvas):
-            for blk in blocks:
-                x = blk.forward_nhwc(x)
+            for j, blk in enumerate(blocks):
+                x = blk.forward_nhwc(x, out=out if j == len(blocks) - 1 else None)
             return x
         from ...engine import act_fmt
-        out = ops.act_empty(x.N, Ho, Wo, blocks[-1].out_channels, act_fmt(), x.device)
+        if out is None:
+            out = ops.act_empty(x.N, Ho, Wo, blocks[-1].out_channels, act_fmt(), x.device)
         for a in range(x.N):
             xi = x.image(a)
             for j, blk in enumerate(blocks):
                 xi = blk.forward_nhwc(xi, out=out.image(a) if j == len(blocks) - 1 else None)
         return out
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, outs=None):
+        """`outs[i]` (optional): caller-owned Act the LAST block of level i writes into (e.g. a slot of the all-gather buffer)."""
         feats = []
         for i in range(self.layernum):
-            x = self._run_level(getattr(self, f"layer{i}"), x)
+            x = self._run_level(getattr(self, f"layer{i}"), x, out=outs[i] if outs is not None else None)
             feats.append(x)
         return feats
 

@@ -29,7 +29,15 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _stream():
+    """Current stream of the CURRENT device.  Every public wrapper runs under `_on(tensor)` (see below), which makes the
+    tensors' device current first, so the launch, the stream and the per-device kernel attributes all agree."""
     return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _on(t):
+    """Context manager: make `t`'s device current for the duration of a C-ABI call (the library launches on the current device)."""
+    dev = t.device if hasattr(t, "device") else t
+    return torch.cuda.device(dev)
 
 
 def _need_cuda(*ts):
@@ -54,8 +62,11 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, name, work=0.0):
-        self.name, self.work = name, work
+    """`work` = algorithmic FLOPs, `nbytes` = algorithmic HBM bytes of the call (SURVEY.md 8d formulas); either may be a
+    zero-argument callable that is evaluated after the instrumented pass has synchronised (data-dependent sizes)."""
+
+    def __init__(self, name, work=0.0, nbytes=0.0):
+        self.name, self.work, self.nbytes = name, work, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -67,17 +78,25 @@ class _Prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.b.record()
-            PROFILE.append((self.name, float(self.work), self.a, self.b))
+            PROFILE.append((self.name, self.work, self.a, self.b, self.nbytes))
         return False
 
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    key = (dev.type, dev.index)
+    """Scratch for one C-ABI call.  Eager calls share one growable buffer per (device, stream).  While a CUDA graph is being
+    captured the buffer is a fresh allocation from the graph's private pool instead: a captured kernel's scratch pointer is
+    baked into the graph, so it must never be the shared buffer that a later, larger eager call replaces and frees."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
         _WS[key] = ws
     return ws
+
+
+BPE = {"f32": 4, "bf16": 2, "split": 4}     # bytes per activation element by storage format
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,6 +138,11 @@ class Act:
     def image(self, b: int) -> "Act":
         return self.images(b, b + 1)
 
+    def rows(self, a: int, b: int) -> "Act":
+        """Rows [a, b) of a single-image map as a zero-copy view (rows of a channels-last image are contiguous)."""
+        assert self.N == 1 and 0 <= a < b <= self.H
+        return Act(self.t[:, a:b] if self.fmt == "f32" else self.t[:, :, a:b], self.fmt)
+
 
 def act_empty(N, H, W, C, fmt: str, device) -> Act:
     if fmt == "f32":
@@ -131,7 +155,7 @@ def convert(a: Act, fmt: str) -> Act:
         return a
     out = act_empty(a.N, a.H, a.W, a.C, fmt, a.device)
     sv, dv = a.view(), out.view()
-    with _Prof("act_convert"):
+    with _Prof("act_convert", 0, a.N * a.H * a.W * float(a.C) * (BPE[a.fmt] + BPE[fmt])):
         rc = lib.heal_act_convert(ctypes.byref(sv), ctypes.byref(dv), a.N * a.H * a.W, a.C, _stream())
     check(rc, "heal_act_convert")
     return out
@@ -204,7 +228,7 @@ def voxelize(points: torch.Tensor, agent_offsets: torch.Tensor, lidar_range, vox
     nvox = torch.zeros((1 + A,), dtype=torch.int32, device=dev)
     ws_bytes = lib.heal_voxelize_workspace(P, cap, A)
     ws = _workspace(dev, ws_bytes)
-    with _Prof("voxelize"):
+    with _Prof("voxelize", 0, lambda: 16.0 * P + float(nvox[0].item()) * (16 * T + 20)):
         rc = lib.heal_voxelize(_p(points), _p(agent_offsets), A, P,
                                _host_f32(lidar_range[0:3]), _host_f32(voxel_size), _host_i32(grid),
                                T, int(max_voxels), cap, _p(voxels), _p(coords), _p(npts), _p(nvox),
@@ -224,7 +248,9 @@ def mean_vfe(voxels: torch.Tensor, num_points: torch.Tensor) -> torch.Tensor:
     assert C == 4 and voxels.dtype == torch.float32 and voxels.is_contiguous()
     npts = num_points.to(torch.int32).contiguous()
     out = torch.empty((M, 4), dtype=torch.float32, device=voxels.device)
-    check(lib.heal_mean_vfe(_p(voxels), _p(npts), M, T, _p(out), _stream()), "heal_mean_vfe")
+    with _Prof("mean_vfe", 0, M * (T * 16.0 + 4 + 16)):
+        rc = lib.heal_mean_vfe(_p(voxels), _p(npts), M, T, _p(out), _stream())
+    check(rc, "heal_mean_vfe")
     return out
 
 
@@ -256,7 +282,16 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
     pf = torch.empty((M, cout), dtype=torch.float32, device=dev) if want_pillar_features else None
     vs = [float(v) for v in voxel_size]
     off = [vs[i] / 2 + float(lidar_range[i]) for i in range(3)]
-    with _Prof("pillar_vfe_scatter(+canvas memset)"):
+    def _bytes():
+        m = float(num_voxels_dev[0].item()) if num_voxels_dev is not None else float(M)
+        b = m * (T * 16 + 20)                                   # voxel slots + count + coords
+        if want_pillar_features:
+            b += m * cout * 4
+        if want_canvas:
+            b += float(batch_size) * ny * nx * cout * BPE[canvas_fmt]
+        return b
+    with _Prof("pillar_vfe_scatter" + ("(+canvas memset)" if want_canvas else ""), lambda: 2.0 * T * w_folded.shape[0] * cout *
+               (float(num_voxels_dev[0].item()) if num_voxels_dev is not None else float(M)), _bytes):
         canvas, cview = None, None
         if want_canvas:
             if canvas_fmt == "f32":
@@ -271,6 +306,23 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
                                          _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), cview, _stream())
     check(rc, "heal_pillar_vfe_scatter")
     return pf, canvas
+
+
+def pillar_scatter(pillar_features: torch.Tensor, voxel_coords: torch.Tensor, nx: int, ny: int, batch_size: int,
+                   fmt: str = "f32", num_voxels_dev: Optional[torch.Tensor] = None) -> Act:
+    """Stand-alone PointPillarScatter: (M,C) f32 rows -> Act (B,ny,nx,C) (zero elsewhere)."""
+    _need_cuda(pillar_features, voxel_coords)
+    M, C = pillar_features.shape
+    coords = voxel_coords.to(torch.int32).contiguous()
+    with _Prof("pillar_scatter(+canvas memset)", 0, M * (C * 4.0 + 16) + batch_size * float(ny) * nx * C * BPE[fmt]):
+        if fmt == "f32":
+            canvas = Act(torch.zeros((batch_size, ny, nx, C), dtype=torch.float32, device=coords.device), "f32")
+        else:
+            canvas = Act(torch.zeros((2 if fmt == "split" else 1, batch_size, ny, nx, C), dtype=torch.bfloat16, device=coords.device), fmt)
+        cv = canvas.view()
+        rc = lib.heal_pillar_scatter(_p(pillar_features), _p(coords), _p(num_voxels_dev), M, C, int(nx), int(ny), ctypes.byref(cv), _stream())
+    check(rc, "heal_pillar_scatter")
+    return canvas
 
 
 # ------------------------------------------------------------------------------------------------
@@ -450,7 +502,9 @@ def conv2d_simt(x: Act, pc: PackedConv, residual: Optional[Act] = None, out: Opt
     st = _stream()
     fam = ("conv_grouped3x3_simt" if pc.groups > 1 else f"conv_dense{pc.kh}x{pc.kw}_simt")
     flops = 2.0 * N * Ho * Wo * pc.cout * (cin // pc.groups) * pc.kh * pc.kw * up * up
-    with _Prof(fam, flops):
+    nbytes = N * H * W * cin * BPE[x.fmt] + N * out.H * out.W * pc.cout * BPE[out.fmt] + pc.weight.numel() * 4.0 \
+        + (N * out.H * out.W * pc.cout * BPE[residual.fmt] if residual is not None else 0)
+    with _Prof(fam, flops, nbytes):
         for i in range(up):
             for j in range(up):
                 wptr = pc.weight if up == 1 else pc.weight[i, j]
@@ -485,7 +539,12 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
             res_split, res_cs, res_plane = residual.t, residual.cstride, residual.plane_stride
     fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "") + ("_grouped" if pc.blockdiag else "") + (f"_s{pc.stride}" if pc.stride > 1 else "")
     flops = 2.0 * N * Ho * Wo * pc.cout * (pc.cin // pc.groups) * pc.kh * pc.kw * up * up
-    with _Prof(fam, flops):
+    epb = 2.0 * pc.planes
+    nbytes = N * H * W * pc.cin * epb + (pc.w_diag if pc.w_diag is not None else pc.w).numel() * 2.0 \
+        + (N * Ho * Wo * up * up * pc.cout * epb if out is not None else 0) \
+        + (N * Ho * Wo * up * up * pc.cout * 4.0 if out_f32 is not None else 0) \
+        + (N * Ho * Wo * up * up * pc.cout * BPE[residual.fmt] if residual is not None else 0)
+    with _Prof(fam, flops, nbytes):
         rc = lib.heal_conv2d_tc(_p(x.t), x.plane_stride, N, H, W, pc.cin, x.cstride, in_coffset,
                                 _p(pc.w), _p(pc.w_diag), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.stride, pc.pad,
                                 1 if pc.blockdiag else 0, pc.planes,
@@ -504,20 +563,32 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
 # ------------------------------------------------------------------------------------------------
 def pyramid_fuse_level(feat: Act, occ: torch.Tensor, theta: torch.Tensor, align_corners: bool,
                        crop_windows: Optional[torch.Tensor] = None, out: Optional[Act] = None,
-                       out_fmt: Optional[str] = None, out_coffset: int = 0) -> Act:
-    """feat: Act (n,H,W,C); occ (n,H,W) f32 logits; theta (n,2,3) f64 -> out Act (1,H,W,C) (one scene)."""
+                       out_fmt: Optional[str] = None, out_coffset: int = 0,
+                       agent_offsets=None, n_agents: Optional[int] = None, rows=None) -> Act:
+    """feat: Act (n,H,W,C); occ (n,H,W) f32 logits; theta (n,2,3) f64 -> out Act (1,H,W,C) (one scene).
+    agent_offsets = (feat element offsets, occ float offsets) per agent when the maps are NOT a dense stack (they live inside
+    an all-gathered buffer: `feat` then describes ONE agent's map geometry at the buffer base and `n_agents` gives n);
+    rows = (row0, nrows): produce only that slab of output rows (out is then (1,nrows,W,C))."""
     _need_cuda(occ, theta)
-    n, H, W, C = feat.N, feat.H, feat.W, feat.C
-    assert occ.is_contiguous() and occ.dtype == torch.float32 and occ.numel() == n * H * W
+    n, H, W, C = (feat.N if n_agents is None else n_agents), feat.H, feat.W, feat.C
+    assert occ.dtype == torch.float32
+    if agent_offsets is None:
+        assert occ.is_contiguous() and occ.numel() == n * H * W
     th = theta.to(torch.float64).contiguous()
     assert th.shape == (n, 2, 3)
+    row0, nrows = rows if rows is not None else (0, H)
     if out is None:
-        out = act_empty(1, H, W, C, out_fmt or feat.fmt, feat.device)
+        out = act_empty(1, nrows, W, C, out_fmt or feat.fmt, feat.device)
+    assert out.H == nrows and out.W == W
     cw = crop_windows.to(torch.int32).contiguous() if crop_windows is not None else None
     fv, ov = feat.view(), out.view(out_coffset)
-    with _Prof("pyramid_fuse_level"):
+    fo = oo = None
+    if agent_offsets is not None:
+        fo = (ctypes.c_longlong * n)(*[int(v) for v in agent_offsets[0]])
+        oo = (ctypes.c_longlong * n)(*[int(v) for v in agent_offsets[1]])
+    with _Prof("pyramid_fuse_level", 0, (n * (C * BPE[feat.fmt] + 4.0) + C * BPE[out.fmt]) * float(nrows) * W):
         rc = lib.heal_pyramid_fuse_level(ctypes.byref(fv), _p(occ), _p(th), _p(cw), n, H, W, C,
-                                         1 if align_corners else 0, ctypes.byref(ov), _stream())
+                                         1 if align_corners else 0, fo, oo, int(row0), int(nrows), ctypes.byref(ov), _stream())
     check(rc, "heal_pyramid_fuse_level")
     return out
 
@@ -530,7 +601,7 @@ def att_fuse(feat: Act, theta: torch.Tensor, out: Optional[Act] = None, out_fmt:
     if out is None:
         out = act_empty(1, H, W, C, out_fmt or feat.fmt, feat.device)
     fv, ov = feat.view(), out.view()
-    with _Prof("att_fuse"):
+    with _Prof("att_fuse", 4.0 * n * C * H * W, (n * BPE[feat.fmt] + BPE[out.fmt]) * float(C) * H * W):
         rc = lib.heal_att_fuse(ctypes.byref(fv), _p(th), n, H, W, C, ctypes.byref(ov), _stream())
     check(rc, "heal_att_fuse")
     return out
@@ -545,7 +616,7 @@ def lss_cell_index(frustum, post_rots_inv, post_trans, combine, trans, lower, dx
     D, fH, fW, _ = frustum.shape
     BN = post_trans.shape[0]
     cell = torch.empty((BN, D, fH, fW), dtype=torch.int32, device=frustum.device)
-    with _Prof("lss_cell_index"):
+    with _Prof("lss_cell_index", 0, BN * D * fH * fW * 4.0 + D * fH * fW * 12.0):
         rc = lib.heal_lss_cell_index(_p(frustum.contiguous().float()), D, fH, fW, _p(post_rots_inv.contiguous().float()),
                                      _p(post_trans.contiguous().float()), _p(combine.contiguous().float()),
                                      _p(trans.contiguous().float()), BN, _host_f32(lower), _host_f32(dx), _host_i32(nx),
@@ -560,7 +631,8 @@ def lss_pool(depth_logits, feat, cell, cams_per_agent: int, nx, ny) -> Act:
     BN, D, fH, fW = depth_logits.shape
     C = feat.shape[1]
     agents = BN // cams_per_agent
-    with _Prof("lss_pool(+bev memset)"):
+    with _Prof("lss_pool(+bev memset)", 2.0 * BN * D * fH * fW * C,
+               BN * fH * fW * 4.0 * (2 * D + C) + agents * float(ny) * nx * C * 4):
         out = torch.zeros((agents, ny, nx, C), dtype=torch.float32, device=feat.device)
         rc = lib.heal_lss_pool(_p(depth_logits.contiguous().float()), _p(feat.contiguous().float()), _p(cell.contiguous()),
                                BN, cams_per_agent, D, C, fH, fW, nx * ny, _p(out), _stream())
@@ -653,7 +725,11 @@ def sp_gather_gemm(feats: torch.Tensor, nbr: torch.Tensor, rows_dev, weight: tor
     Kw, cin, cout = weight.shape
     assert Kw == K and feats.shape[1] == cin and feats.is_contiguous()
     out = torch.empty((cap, cout), dtype=torch.float32, device=feats.device)
-    with _Prof("spconv_gather_gemm", 2.0 * cap * K * cin * cout):
+    def _pairs():
+        m = cap if rows_dev is None else min(cap, int(rows_dev[0].item()))
+        return float((nbr[:m] >= 0).sum().item()), float(m)
+    with _Prof("spconv_gather_gemm", lambda: 2.0 * _pairs()[0] * cin * cout,
+               lambda: _pairs()[0] * (cin * 4.0 + 4.0) + _pairs()[1] * (cout * 4.0 + K * 4.0)):
         rc = lib.heal_spconv_gather_gemm(_p(feats), _p(nbr), _p(rows_dev), cap, K, _p(weight), _p(bias), cin, cout,
                                          1 if relu else 0, _p(out), _stream())
     check(rc, "heal_spconv_gather_gemm")
@@ -664,7 +740,7 @@ def sparse_to_bev(st: SparseTensor) -> Act:
     """HeightCompression: (B, H, W, C*D) channels-last fp32 with channel = c*D + z."""
     D, H, W = st.spatial_shape
     C = st.feats.shape[1]
-    with _Prof("sparse_to_bev(+memset)"):
+    with _Prof("sparse_to_bev(+memset)", 0, st.batch * float(H) * W * C * D * 4 + st.capacity * (C * 4.0 + 16)):
         out = torch.zeros((st.batch, H, W, C * D), dtype=torch.float32, device=st.feats.device)
         rc = lib.heal_sparse_to_bev(_p(st.feats), _p(st.coords), _p(st.rows_dev), st.capacity, C, D, H, W, _p(out), _stream())
     check(rc, "heal_sparse_to_bev")
@@ -699,7 +775,7 @@ def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, 
                                nx, ny, batch_size, want_pillar_features=True, want_canvas=False, num_voxels_dev=num_voxels_dev)
     coords = voxel_coords.to(torch.int32).contiguous()
     idmap = torch.empty((batch_size, ny, nx), dtype=torch.int32, device=pf.device)
-    with _Prof("pillar_idmap"):
+    with _Prof("pillar_idmap", 0, batch_size * float(ny) * nx * 4 + coords.shape[0] * 16.0):
         rc = lib.heal_pillar_idmap(_p(coords), _p(num_voxels_dev), coords.shape[0], batch_size, ny, nx, _p(idmap), _stream())
     check(rc, "heal_pillar_idmap")
 
@@ -720,7 +796,11 @@ def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_
     o2 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
     v1, v2 = o1.view(), o2.view()
     fn = lib.heal_sparse_stem_tc if (tensor_cores and sc.W % 32 == 0) else lib.heal_sparse_stem
-    with _Prof("sparse_stem", 0):
+    def _stem():
+        hits = float((sc.idmap >= 0).sum().item())
+        return hits
+    with _Prof("sparse_stem", lambda: 2.0 * 64 * 64 * (2.25 + 0.25) * _stem(),
+               lambda: sc.N * float(sc.H) * sc.W * 4 + _stem() * 256.0 + 2.0 * sc.N * (sc.H // 2) * (sc.W // 2) * 64 * BPE[out_fmt]):
         rc = fn(_p(sc.feats), _p(sc.idmap), sc.N, sc.H, sc.W, _p(pc_conv.weight), _p(pc_conv.bias),
                 _p(pc_down.weight), _p(pc_down.bias), 64, ctypes.byref(v1), ctypes.byref(v2), _stream())
     check(rc, "heal_sparse_stem")
@@ -779,3 +859,46 @@ def box_decode_nms(cls_preds, reg_preds, dir_preds, anchors: torch.Tensor, trans
                                      _p(buffers.workspace), buffers.workspace.numel(), _stream())
     check(rc, "heal_box_decode_nms")
     return buffers
+
+
+# ------------------------------------------------------------------------------------------------
+# device guard: the library launches on the CURRENT device and on the stream passed in; every public wrapper therefore runs
+# with its tensors' device made current (a model on cuda:1 while cuda:0 is current, or one process driving two GPUs).
+# ------------------------------------------------------------------------------------------------
+import functools as _functools
+
+
+def _device_of(x):
+    if isinstance(x, torch.Tensor):
+        return x.device if x.is_cuda else None
+    if isinstance(x, (Act, SparseCanvas)):
+        return x.device
+    if isinstance(x, SparseTensor):
+        return x.coords.device
+    return None
+
+
+def _guard(fn):
+    @_functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in args:
+            dev = _device_of(a)
+            if dev is not None:
+                break
+        if dev is None:
+            for a in kwargs.values():
+                dev = _device_of(a)
+                if dev is not None:
+                    break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+for _name in ("convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
+              "lss_cell_index", "lss_pool", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sparse_to_bev",
+              "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
+    globals()[_name] = _guard(globals()[_name])

@@ -138,3 +138,247 @@ def forward_agent_sharded(model, data_dict, rank: int, world: int):
     cls, reg, dirp = model._heads(f)
     return {'pyramid': 'collab', 'cls_preds': cls, 'reg_preds': reg, 'dir_preds': dirp,
             'occ_single_list': [o.unsqueeze(1) for o in g_occs]}
+
+
+# ======================================================================================================================
+# Graph-captured agent-per-GPU frame (variant B) with a row-sharded fusion tail
+# ======================================================================================================================
+def rank_layout(level_shapes: Sequence[Tuple[int, int, int]], planes: int, slots: int):
+    """Byte layout of ONE rank's chunk of the symmetric gather buffer: for every pyramid level a dense
+    (planes, slots, H, W, C) bf16 block (fp32 storage: planes = 2 worth of bytes), then per level a (slots, H, W) fp32 occupancy
+    block.  Level-major inside the chunk so that a rank's local agents form ordinary dense `Act`s the conv epilogues write into.
+    Returns (feat byte offsets, occ byte offsets, chunk bytes padded to 256)."""
+    foffs, ooffs, o = [], [], 0
+    for (h, w, c) in level_shapes:
+        foffs.append(o)
+        o += planes * slots * h * w * c * 2
+    for (h, w, c) in level_shapes:
+        ooffs.append(o)
+        o += slots * h * w * 4
+    return foffs, ooffs, (o + 255) // 256 * 256
+
+
+def agent_offsets_in_gather(plan, level_shapes, planes: int, slots: int, elem_bytes: int = 2):
+    """For every level: (feature element offsets, occupancy float offsets) of each REAL agent, in scene order, from the base of
+    the gathered (world, chunk) buffer -- the table heal_pyramid_fuse_level reads the agents through (no unpack copy)."""
+    foffs, ooffs, chunk = rank_layout(level_shapes, planes, slots)
+    table = []
+    for li, (h, w, c) in enumerate(level_shapes):
+        fo, oo = [], []
+        for r, agents in enumerate(plan):
+            for s in range(len(agents)):
+                fo.append((r * chunk + foffs[li]) // elem_bytes + s * h * w * c)
+                oo.append((r * chunk + ooffs[li]) // 4 + s * h * w)
+        table.append((fo, oo))
+    return table
+
+
+def tail_rows(H: int, rank: int, world: int):
+    """Row partition of the fused map for the replicated tail (deblocks -> shrink 3x3 x2 -> heads): rank r produces head rows
+    [r0, r1); it needs the second 3x3's input rows [b0, b1) = [r0-1, r1+1) and the first 3x3's input (the 384-channel concat)
+    rows [c0, c1) = [r0-2, r1+2) rounded out to multiples of 4 (the coarsest pyramid level is 4x smaller), all clamped to the map.
+    Returns None when H does not split evenly (callers then run the tail replicated)."""
+    if world < 2 or H % world or (H // world) % 4:
+        return None
+    per = H // world
+    r0, r1 = rank * per, (rank + 1) * per
+    c0, c1 = max(0, (r0 - 2) // 4 * 4), min(H, -(-(r1 + 2) // 4) * 4)
+    b0, b1 = max(0, r0 - 1), min(H, r1 + 1)
+    return {"r": (r0, r1), "b": (b0, b1), "c": (c0, c1)}
+
+
+class AgentShardedFrame:
+    """One scene, agents sharded over `world` ranks, captured as ONE CUDA graph per rank:
+
+        voxelize -> PillarVFE -> per-agent ResNet -> ResNeXt levels + occupancy heads      (my agents; the last conv of every
+                                                                                             level and the occupancy heads write
+                                                                                             straight into my chunk of the
+                                                                                             symmetric gather buffer)
+        ncclAllGather (in place)                                                            the ONE exchange of BEV feature maps
+        warp + weighted fuse x3 -> deblocks -> shrink 3x3 x2 -> heads                      for MY slab of output rows only, read
+                                                                                             straight from the gathered buffer
+        ncclAllGather of the head rows (5 MB in total)                                      every rank ends with the full heads
+
+    No torch.cat / index_select / permute copies on the data path.  `load_scene` copies only this rank's agents' points."""
+
+    def __init__(self, model, n_agents: int, rank: int, world: int, point_capacity: int, pairwise_shape, device=None,
+                 modality: str = "m1", shard_tail: bool = True, group=None, warmup: int = 2):
+        from . import ops
+        from .engine import act_fmt
+        from ._lib import lib
+        dev = device or next(model.parameters()).device
+        self.model, self.rank, self.world, self.dev, self.group = model, rank, world, dev, group
+        self.n_agents, self.m = n_agents, modality
+        self.plan = agent_plan(n_agents, world)
+        self.slots = len(self.plan[0])
+        self.mine = self.plan[rank]
+        pb = model.pyramid_backbone
+        fmt = act_fmt()
+        self.fmt = fmt
+        planes = 2 if fmt in ("split", "f32") else 1            # f32 storage = two bf16 planes worth of bytes
+        H0 = int(round((model.cav_range[4] - model.cav_range[1]) / model.args[modality]['encoder_args']['voxel_size'][1])) // 2
+        W0 = int(round((model.cav_range[3] - model.cav_range[0]) / model.args[modality]['encoder_args']['voxel_size'][0])) // 2
+        nf = pb.model_cfg['num_filters']
+        strides = pb.model_cfg['layer_strides']
+        shapes, h, w = [], H0, W0
+        for c, s in zip(nf, strides):
+            h, w = (h - 1) // s + 1, (w - 1) // s + 1
+            shapes.append((h, w, c))
+        self.level_shapes = shapes
+        self.foffs, self.ooffs, self.chunk = rank_layout(shapes, planes, self.slots)
+        self.gather = torch.zeros((world, self.chunk), dtype=torch.uint8, device=dev)
+        self.table = agent_offsets_in_gather(self.plan, shapes, planes, self.slots, 4 if fmt == "f32" else 2)
+        mychunk = self.gather[rank]
+        S = self.slots
+        self.level_out, self.occ_out = [], []
+        for (h, w, c), fo, oo in zip(shapes, self.foffs, self.ooffs):
+            if fmt == "f32":
+                t = mychunk[fo:fo + S * h * w * c * 4].view(torch.float32).view(S, h, w, c)
+            else:
+                t = mychunk[fo:fo + planes * S * h * w * c * 2].view(torch.bfloat16).view(planes, S, h, w, c)
+            self.level_out.append(ops.Act(t, fmt))
+            self.occ_out.append(ops.Act(mychunk[oo:oo + S * h * w * 4].view(torch.float32).view(S, h, w, 1), "f32"))
+        # static inputs: my agents' points (idle slots = empty clouds), their offsets, the scene's pairwise matrix
+        self.cap = point_capacity
+        self.points = torch.zeros((point_capacity, 4), dtype=torch.float32, device=dev)
+        self.offsets = torch.zeros((S + 1,), dtype=torch.int32, device=dev)
+        self.pairwise = torch.zeros(tuple(pairwise_shape), dtype=torch.float64, device=dev)
+        self.pairwise.copy_(torch.eye(4, dtype=torch.float64, device=dev).expand(self.pairwise.shape))
+        self._offs_ring = [torch.zeros((S + 1,), dtype=torch.int32).pin_memory() for _ in range(8)]
+        self._ring_i = 0
+        # tail partition + output buffers
+        self.Hf, self.Wf = shapes[0][0], shapes[0][1]
+        self.rows = tail_rows(self.Hf, rank, world) if shard_tail else None
+        self.tail_mode = ("row-sharded (rows %d..%d of %d per rank) + all-gather of the head rows" % (self.rows["r"][0], self.rows["r"][1], self.Hf)
+                          if self.rows else "replicated on every rank")
+        self.n_head = model.cls_head.out_channels + model.reg_head.out_channels + model.dir_head.out_channels
+        self.heads = torch.zeros((1, self.Hf, self.Wf, self.n_head), dtype=torch.float32, device=dev)
+        self.collectives_per_frame = 2 if (self.rows and world > 1) else (1 if world > 1 else 0)
+        # capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self._frame()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=group)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = lib.heal_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self._frame()
+        self.kernels_per_replay = int(lib.heal_launch_count() - l0)
+
+    # ---- host side --------------------------------------------------------------------------------------------------
+    def load_scene(self, points: torch.Tensor, offsets_host, pairwise: torch.Tensor):
+        """points: the WHOLE scene's (P,4) clouds (device or pinned host), offsets_host: (n_agents+1) python/numpy ints.
+        Only this rank's agents are copied; idle slots (and an idle rank) get empty clouds."""
+        offs = [int(v) for v in offsets_host]
+        S = self.slots
+        if self.mine:
+            lo, hi = offs[self.mine[0]], offs[self.mine[-1] + 1]
+            local = [offs[a] - lo for a in self.mine] + [hi - lo]
+        else:
+            lo = hi = 0
+            local = [0]
+        local = local + [local[-1]] * (S + 1 - len(local))
+        if hi - lo > self.cap:
+            raise ValueError(f"{hi - lo} points for this rank, capacity {self.cap}")
+        if hi > lo:
+            self.points[:hi - lo].copy_(points[lo:hi], non_blocking=True)
+        stage = self._offs_ring[self._ring_i]
+        self._ring_i = (self._ring_i + 1) % len(self._offs_ring)
+        stage.copy_(torch.tensor(local, dtype=torch.int32))
+        self.offsets.copy_(stage, non_blocking=True)
+        self.pairwise.copy_(pairwise, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    # ---- the frame (captured) ---------------------------------------------------------------------------------------
+    def _all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        if self.world > 1:
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def _frame(self):
+        from . import ops
+        from .engine import conv_bn_act, act_fmt
+        from .utils.transformation_utils import normalize_pairwise_tfm
+        from .models.sub_modules.base_bev_backbone_resnet import decode_levels
+        model, m = self.model, self.m
+        pb = model.pyramid_backbone
+        enc, bb = getattr(model, f"encoder_{m}"), getattr(model, f"backbone_{m}")
+        sub = {f'inputs_{m}': {'points': self.points, 'agent_offsets': self.offsets}}
+        x = enc.forward_act(sub, m)
+        x = bb.decode_nhwc(bb.multiscale_nhwc(x))
+        feats = pb.multiscale_nhwc(x, outs=self.level_out)              # last conv of each level -> my chunk of the gather buffer
+        for i, f in enumerate(feats):
+            pb._occ_nhwc(f, i, out=self.occ_out[i])
+        # ---- the one exchange of BEV feature maps ----
+        self._all_gather(self.gather.view(-1), self.gather[self.rank])
+        affine = normalize_pairwise_tfm(self.pairwise, model.H, model.W, model.fake_voxel_size)
+        theta = affine[0, 0, :self.n_agents].contiguous()
+        occ_base = self.gather.view(-1).view(torch.float32)
+        fmt = self.fmt
+        fused = []
+        rows = self.rows
+        for li, (h, w, c) in enumerate(self.level_shapes):
+            base = self.gather.view(-1)
+            S = self.slots
+            if fmt == "f32":
+                geo = ops.Act(base[:h * w * c * 4].view(torch.float32).view(1, h, w, c), "f32")
+            else:
+                planes = 2 if fmt == "split" else 1
+                # geometry of ONE agent's map at the buffer base; plane stride = slots*h*w*c elements (level-major chunk layout)
+                t = torch.as_strided(base.view(torch.bfloat16), (planes, 1, h, w, c), (S * h * w * c, h * w * c, w * c, c, 1))
+                geo = ops.Act(t, fmt)
+            sc = self.Hf // h
+            rr = (rows["c"][0] // sc, (rows["c"][1] - rows["c"][0]) // sc) if rows else None
+            fused.append(ops.pyramid_fuse_level(geo, occ_base, theta, pb.align_corners, None, out_fmt=fmt,
+                                                agent_offsets=self.table[li], n_agents=self.n_agents, rows=rr))
+        f = decode_levels(pb.deblocks, fused)                          # (1, c1-c0 | H, W, 384)
+        dc = model.shrink_conv.layers[0].double_conv if model.shrink_flag else None
+        if rows is None:
+            if model.shrink_flag:
+                f = model.shrink_conv.forward_nhwc(f)
+            self._head_conv(f, self.heads_act())
+        else:
+            assert model.shrink_flag and len(model.shrink_conv.layers) == 1, "row-sharded tail expects the single DoubleConv shrink header"
+            (r0, r1), (b0, b1), (c0, c1) = rows["r"], rows["b"], rows["c"]
+            a = conv_bn_act(f, dc[0], None, relu=True)                 # rows [c0, c1); valid on [c0+1, c1-1) (or to the map border)
+            b = conv_bn_act(a.rows(b0 - c0, b1 - c0), dc[2], None, relu=True)   # rows [b0, b1); valid on [r0, r1)
+            self._head_conv(b.rows(r0 - b0, r1 - b0), self.heads_act().rows(r0, r1))
+            self._all_gather(self.heads.view(-1), self.heads[0, r0:r1].reshape(-1))
+        o, outs = 0, {}
+        for name, head in (("cls_preds", model.cls_head), ("reg_preds", model.reg_head), ("dir_preds", model.dir_head)):
+            outs[name] = self.heads[..., o:o + head.out_channels].permute(0, 3, 1, 2).contiguous()
+            o += head.out_channels
+        outs['pyramid'] = 'collab'
+        return outs
+
+    def heads_act(self):
+        from . import ops
+        return ops.Act(self.heads, "f32")
+
+    def _head_conv(self, x, out_act):
+        from .engine import conv_bn_act
+        fh = self.model._heads
+        fh.prepare()
+        conv_bn_act(x, fh._conv, None, relu=False, out=out_act, out_fmt="f32")
+
+    def time_allgather(self, iters: int = 20):
+        """The BEV all-gather alone (same buffers, outside the graph): CUDA-event ms per call on this rank."""
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for _ in range(3):
+            self._all_gather(self.gather.view(-1), self.gather[self.rank])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            self._all_gather(self.gather.view(-1), self.gather[self.rank])
+        b.record()
+        torch.cuda.synchronize(self.dev)
+        return {"ms": a.elapsed_time(b) / iters, "bytes_per_rank": int(self.chunk)}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HEAL_B200_ABI_VERSION 2
+#define HEAL_B200_ABI_VERSION 3
 
 /* Activation tensor view (channels-last).  fmt: 0 = fp32, 1 = bf16 (one plane), 2 = split-bf16
  * (hi = bf16(x) at data, lo = bf16(x-hi) at data + plane_stride elements; x ~ hi+lo, 16 mantissa bits).
@@ -81,6 +81,11 @@ int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_po
                             const float* w_folded, const float* b_folded, int c_in, int c_out,
                             const float* voxel_size3_host, const float* offset3_host, int nx, int ny,
                             float* pillar_features_out, const heal_act_t* canvas_out, void* stream);
+
+/* Stand-alone PointPillarScatter.forward (opencood/models/sub_modules/point_pillar_scatter.py:19-77): rows of pillar features
+ * (M,channels) f32 -> canvas cell [b][y][x + z] of a pre-zeroed channels-last canvas view (any storage format). */
+int heal_pillar_scatter(const float* pillar_features, const int* voxel_coords, const int* num_voxels_dev, int num_voxels,
+                        int channels, int nx, int ny, const heal_act_t* canvas_out, void* stream);
 
 /* ---- sparse stem: scatter + the first residual block's two stride-2 convs straight from the pillar list -------------
  * heal_pillar_idmap: (B,ny,nx) i32 map, cell -> pillar row or -1 (replaces the dense canvas of PointPillarScatter,
@@ -146,10 +151,16 @@ int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, i
  * (:145) and the eval-mode camera crop mask (:147-162) for ONE scene.
  *   feat (n,H,W,C) channels-last; occ (n,H,W) logits; theta (n,2,3) f64 = affine_matrix[b,0,:n]
  *   crop_windows (n,4) i32 [h0,h1,w0,w1] (score kept inside, zeroed outside) or NULL
- *   out (H,W,C) */
+ *   agent_feat_offsets_host / agent_occ_offsets_host: HOST arrays of n element offsets of agent j's feature map (from
+ *     feat->data, in elements of the storage type) and occupancy map (from occ, in floats); NULL = dense stacks
+ *     (j*H*W*cstride, j*H*W).  This is how the kernel reads the agents straight out of the all-gathered buffer of the
+ *     agent-per-GPU partition without an unpack copy.
+ *   row0, rows: produce output rows [row0, row0+rows) only (row-sharded fusion tail); rows <= 0 = the whole map
+ *   out (rows,W,C): the output slab, its pixel 0 is (row0, 0) */
 int heal_pyramid_fuse_level(const heal_act_t* feat, const float* occ, const double* theta,
                             const int* crop_windows, int n_agents, int H, int W, int C, int align_corners,
-                            const heal_act_t* out, void* stream);
+                            const long long* agent_feat_offsets_host, const long long* agent_occ_offsets_host,
+                            int row0, int rows, const heal_act_t* out, void* stream);
 
 /* AttFusion.forward for one scene (opencood/models/fuse_modules/fusion_in_one.py:126-151) */
 int heal_att_fuse(const heal_act_t* feat, const double* theta, int n_agents, int H, int W, int C,

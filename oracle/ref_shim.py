@@ -1,9 +1,9 @@
-"""Import shim for the UNMODIFIED reference (yifanlu0227/HEAL) mounted at /root/reference.
+"""Import shim for the UNMODIFIED reference (yifanlu0227/HEAL).
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py, in the build container, to run the
-reference's own PyTorch modules on CPU and dump golden vectors under tests/golden/.  Nothing under
-heal_b200/ imports this file, and nothing that runs on the GPU box does (/root/reference does not
-exist there).
+TEST INFRASTRUCTURE ONLY.  The reference package is imported from `oracle/_ref/` (the byte-for-byte copy made by
+`oracle/build_ref.py`; git-ignored, travels to the GPU box) or, in the build container, straight from /root/reference.
+Users: oracle/make_golden.py (golden vectors), oracle/ref_runner.py (bench.py's reference arm and baseline legs) and the
+boundary tests.  Nothing under heal_b200/ imports this file.
 
 The reference imports a handful of cosmetic / absent third-party packages at module top
 (SURVEY.md §8c).  They are replaced by MagicMock stubs; spconv is absent, so every spconv-backed
@@ -14,7 +14,8 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("HEAL_REFERENCE_ROOT", "/root/reference")
+_LOCAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("HEAL_REFERENCE_ROOT") or (_LOCAL if os.path.isdir(os.path.join(_LOCAL, "opencood")) else "/root/reference")
 
 _STUBS = [
     "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "icecream", "termcolor",

@@ -38,6 +38,27 @@ def main():
             ok = ok and same
             if not same:
                 print(f"rank {rank} agents {n_agents} {k}: max diff {(ref[k]-out[k]).abs().max().item():.3e}")
+    # graph-captured partition with the row-sharded tail (AgentShardedFrame): same scene, bit-identical heads on every rank
+    for n_agents in (world, 5):
+        sc = synth.scene(6, n_agents=n_agents, max_cav=max(5, n_agents), rings=16, azimuth=256)
+        offs = np.concatenate([[0], np.cumsum([p.shape[0] for p in sc["points"]])]).astype(np.int32)
+        pts = torch.from_numpy(np.concatenate(sc["points"])).cuda()
+        pw = torch.from_numpy(sc["pairwise_t_matrix"]).cuda()
+        data = {"inputs_m1": {"points": pts, "agent_offsets": torch.from_numpy(offs).cuda()},
+                "agent_modality_list": ["m1"] * n_agents, "record_len": torch.tensor([n_agents]), "pairwise_t_matrix": pw}
+        with torch.no_grad():
+            ref = model(data)
+            for shard_tail in (True, False):
+                sf = parallel.AgentShardedFrame(model, n_agents, rank, world, 1 << 16, tuple(pw.shape), shard_tail=shard_tail)
+                sf.load_scene(pts, offs, pw)
+                out = sf.replay()
+                torch.cuda.synchronize()
+                for k in ("cls_preds", "reg_preds", "dir_preds"):
+                    same = torch.equal(ref[k], out[k])
+                    ok = ok and same
+                    if not same:
+                        print(f"rank {rank} graph agents {n_agents} shard_tail={shard_tail} {k}: max diff {(ref[k]-out[k]).abs().max().item():.3e}")
+                del sf
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(_lib.lib, s), f"{s} declared in include/heal_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in heal_b200/_lib.py"
-    assert _lib.lib.heal_abi_version() == 2
+    assert _lib.lib.heal_abi_version() == 3
     assert _lib.lib.heal_launch_count() == 0
 
 

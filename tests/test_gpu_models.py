@@ -122,6 +122,45 @@ def test_agent_sharded_world1_equals_plain_forward():
         torch.testing.assert_close(a[k], b[k], rtol=0, atol=0)
 
 
+def test_agent_sharded_frame_world1_equals_plain_forward():
+    """AgentShardedFrame (symmetric buffer written by the conv epilogues, fuse kernel reading the agents through the offset table,
+    captured graph) on one rank == the plain module forward, bit for bit."""
+    from heal_b200 import synth, parallel
+    args = make_golden.small_model_args()
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "heter_pyramid_collab_small.pt"), weights_only=False)
+    model, _ = _build(args, g["shapes"])
+    for n_agents in (3, 1):
+        sc = synth.scene(5, n_agents=n_agents, rings=16, azimuth=256)
+        offs = np.concatenate([[0], np.cumsum([p.shape[0] for p in sc["points"]])]).astype(np.int32)
+        pts = torch.from_numpy(np.concatenate(sc["points"])).cuda()
+        pw = torch.from_numpy(sc["pairwise_t_matrix"]).cuda()
+        data = {"inputs_m1": {"points": pts, "agent_offsets": torch.from_numpy(offs).cuda()},
+                "agent_modality_list": ["m1"] * n_agents, "record_len": torch.tensor([n_agents]), "pairwise_t_matrix": pw}
+        with torch.no_grad():
+            a = model(data)
+            sf = parallel.AgentShardedFrame(model, n_agents, 0, 1, 1 << 16, tuple(pw.shape))
+            sf.load_scene(pts, offs, pw)
+            b = sf.replay()
+        torch.cuda.synchronize()
+        for k in ("cls_preds", "reg_preds", "dir_preds"):
+            torch.testing.assert_close(a[k], b[k], rtol=0, atol=0)
+
+
+def test_pyramid_fuse_row_slab_equals_whole_map():
+    """heal_pyramid_fuse_level with (row0, rows) produces exactly the corresponding rows of the whole-map call."""
+    from heal_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    n, H, W, C = 3, 32, 48, 64
+    x = torch.randn(n, H, W, C, generator=gen).cuda()
+    occ = torch.randn(n, H, W, generator=gen).cuda()
+    th = torch.tensor([[[1, 0, 0], [0, 1, 0]], [[0.9, 0.2, 0.1], [-0.2, 0.9, 0.05]], [[0.7, -0.5, -0.2], [0.5, 0.7, 0.1]]], dtype=torch.float64).cuda()
+    for fmt in ("f32", "split"):
+        feat = ops.convert(ops.Act(x, "f32"), fmt)
+        whole = ops.convert(ops.pyramid_fuse_level(feat, occ, th, False), "f32").t
+        slab = ops.convert(ops.pyramid_fuse_level(feat, occ, th, False, rows=(8, 12)), "f32").t
+        assert torch.equal(slab[0], whole[0, 8:20])
+
+
 def test_frame_graph_and_pipeline_equal_eager():
     """CUDA-graph replay (FrameGraph) and the 3-stream serving loop (FramePipeline: copy-in / compute / copy-out overlap, two
     captured frames) return, frame by frame, exactly what the eager module call returns for clouds of different sizes."""

@@ -69,3 +69,65 @@ def test_allgather_roundtrip_world2_balanced():
 def test_allgather_roundtrip_world2_ragged_and_idle():
     _run(5)     # 3 + 2 agents
     _run(1)     # rank 1 idle
+
+
+# ---- graph-captured partition (AgentShardedFrame): symmetric-buffer layout, offset table, tail rows -------------------
+def test_tail_rows_partition_covers_the_map_with_halos():
+    for world in (2, 4, 8):
+        got = []
+        for r in range(world):
+            t = parallel.tail_rows(256, r, world)
+            (r0, r1), (b0, b1), (c0, c1) = t["r"], t["b"], t["c"]
+            assert c0 % 4 == 0 and c1 % 4 == 0 and 0 <= c0 <= b0 <= r0 < r1 <= b1 <= c1 <= 256
+            assert (b0 == 0 or b0 == r0 - 1) and (b1 == 256 or b1 == r1 + 1)
+            assert (c0 == 0 or c0 <= r0 - 2) and (c1 == 256 or c1 >= r1 + 2)          # first 3x3 valid where the second reads it
+            got += list(range(r0, r1))
+        assert got == list(range(256))
+    assert parallel.tail_rows(256, 0, 1) is None and parallel.tail_rows(250, 0, 4) is None
+
+
+def _worker_layout(rank, world, port, n_agents, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = parallel.agent_plan(n_agents, world)
+        slots = len(plan[0])
+        shapes = [(8, 8, 16), (4, 4, 32)]
+        planes = 2
+        foffs, ooffs, chunk = parallel.rank_layout(shapes, planes, slots)
+        gen = torch.Generator().manual_seed(99)
+        truth_f = [torch.randn(n_agents, planes, h, w, c, generator=gen).to(torch.bfloat16) for (h, w, c) in shapes]
+        truth_o = [torch.randn(n_agents, h, w, generator=gen) for (h, w, c) in shapes]
+        buf = torch.zeros((world, chunk), dtype=torch.uint8)
+        mine = plan[rank]
+        for li, (h, w, c) in enumerate(shapes):         # what the conv epilogues do: dense (planes, slots, h, w, c) blocks in MY chunk
+            blk = buf[rank][foffs[li]:foffs[li] + planes * slots * h * w * c * 2].view(torch.bfloat16).view(planes, slots, h, w, c)
+            occ = buf[rank][ooffs[li]:ooffs[li] + slots * h * w * 4].view(torch.float32).view(slots, h, w)
+            for s, a in enumerate(mine):
+                blk[:, s] = truth_f[li][a]
+                occ[s] = truth_o[li][a]
+        dist.all_gather_into_tensor(buf.view(-1), buf[rank].clone())
+        table = parallel.agent_offsets_in_gather(plan, shapes, planes, slots)
+        flat16, flat32 = buf.view(-1).view(torch.bfloat16), buf.view(-1).view(torch.float32)
+        ok = True
+        for li, (h, w, c) in enumerate(shapes):
+            fo, oo = table[li]
+            assert len(fo) == n_agents
+            for a in range(n_agents):
+                for p in range(planes):
+                    got = flat16[fo[a] + p * slots * h * w * c: fo[a] + p * slots * h * w * c + h * w * c].view(h, w, c)
+                    ok = ok and torch.equal(got, truth_f[li][a, p])
+                ok = ok and torch.equal(flat32[oo[a]: oo[a] + h * w].view(h, w), truth_o[li][a])
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_symmetric_buffer_layout_world2():
+    for n_agents in (4, 5, 1):
+        port = _free_port()
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_worker_layout, args=(2, port, n_agents, ret), nprocs=2, join=True)
+        assert dict(ret) == {0: True, 1: True}, n_agents
