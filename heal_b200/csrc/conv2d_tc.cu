@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_prims.cuh"
 #include "../../include/heal_b200.h"
 
 namespace {
@@ -47,7 +48,9 @@ struct TcP {
     int kc_blocks;                // Cin / 64
     int TH, TW, tiles_h, tiles_w; // pixel tile and tile grid per image
     int m_tiles, n_tiles;
-    int planes;                   // 1 = bf16, 2 = split-bf16 (fp32-equivalent)
+    int planes;                   // ACTIVATION planes: 1 = bf16, 2 = split-bf16 (fp32-equivalent)
+    int wplanes;                  // WEIGHT planes: 2 = split weights (hi + lo).  planes 1 + wplanes 2 = the 'bf16' engine mode:
+                                  // bf16 activations x un-rounded (16-mantissa-bit) weights, a_hi x [b_hi | b_lo]
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
     int relu;
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
@@ -64,136 +67,6 @@ struct TcP {
     __nv_bfloat16* out_split; size_t out_plane; int out_cs, out_co;
     float* out_f32; int out32_cs, out32_co;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100): rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address (16 B units)
-    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) = 1
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-    return d;
-}
-
-// K-major, 32B-swizzled descriptor (rows of 32 B = 16 bf16, 8-row groups 256 B apart): the packed diagonal weight sub-blocks.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                           // SWIZZLE_32B
-    return d;
-}
-
-// Same, for a start address that is only 128 B aligned (a ROW offset inside a TMA-written swizzled tile).
-// Measured on B200 (profiles/halo_diag.py): the tensor core applies the 128B swizzle to the ABSOLUTE shared-memory
-// address (bits [4,7) ^= bits [7,10)), exactly like the TMA unit, so a row-shifted view needs no base-offset:
-// the descriptor's base_offset field must stay 0 (setting it to the row phase produces garbage).
-__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, int mode) {
-    uint32_t ph = (saddr >> 7) & 7;
-    uint32_t bo = (mode == 0) ? 0u : ph;      // mode 1 kept only for the diagnostic script
-    return umma_desc_sw128(saddr) | ((uint64_t)bo << 49);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-                 " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// One lane of a converged warp; the compiler keeps code under this predicate on the uniform datapath (the tcgen05 /
-// TMA instructions take uniform-register operands: issuing them from an `if (lane == 0)` region instead costs an
-// ELECT + branch loop per instruction, measured at ~110 cycles per tcgen05.mma).
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred = 0;
-    asm volatile("{\n .reg .b32 rx;\n .reg .pred px;\n elect.sync rx|px, 0xffffffff;\n @px mov.s32 %0, 1;\n}" : "+r"(pred));
-    return pred;
-}
-
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
 
 // STG = number of 64-channel output staging buffers in shared memory (0: the epilogue stores straight to global memory;
 // >0: it writes the swizzled tile to smem and one elected thread issues a TMA tensor store, so every global write is a
@@ -216,7 +89,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // halo mode: A = [plane][TW+2 rows][128 B] (padded to 1 KiB), B = [plane][3 taps][BLOCK_N rows][128 B]
     const int halo_a_plane = (p.TW + 2) * 128;
     const int halo_a_bytes = (p.planes * halo_a_plane + 1023) & ~1023;
-    const int stage_bytes = p.halo ? (halo_a_bytes + p.planes * 3 * B_TILE_BYTES) : p.planes * (A_TILE_BYTES + B_TILE_BYTES);
+    const int stage_bytes = p.halo ? (halo_a_bytes + p.wplanes * 3 * B_TILE_BYTES) : (p.planes * A_TILE_BYTES + p.wplanes * B_TILE_BYTES);
     const int stg_bytes = p.planes * A_TILE_BYTES;                        // one staging buffer: [plane][128 rows][128 B]
     uint8_t* stg = smem + (size_t)STAGES * stage_bytes;                   // 1024-aligned (stage_bytes is a multiple of 1024)
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)STG * stg_bytes);
@@ -280,7 +153,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // k-block = (kernel row tap, channel block): pixels [w0-1, w0+TW] of input row h0+tap-1, and the 3 taps' weights
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + halo_a_bytes;
                         if (elect_one()) {
-                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * (halo_a_plane + 3 * B_TILE_BYTES)));
+                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.planes * halo_a_plane + p.wplanes * 3 * B_TILE_BYTES));
                             tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 - 1, h0 + tap - 1, img, 0);
                             // B lands as [tap][plane][rows] (dense) or [tap][16-row sub-block][plane][16 rows] (block-diagonal)
                             if (p.blockdiag) tma_load_5d(sb, &tmB, bar_full + 8 * stage, 0, 0, 0, nt * (BLOCK_N / 16), tap * 3);
@@ -294,7 +167,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint32_t sb = sa + p.planes * A_TILE_BYTES;
                     const bool ldA = !(p.dbg & 4), ldB = !(p.dbg & 2);
                     if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * stage, (uint32_t)((ldA ? p.planes * A_TILE_BYTES : 0) + (ldB ? p.planes * B_TILE_BYTES : 0)));
+                        mbar_expect_tx(bar_full + 8 * stage, (uint32_t)((ldA ? p.planes * A_TILE_BYTES : 0) + (ldB ? p.wplanes * B_TILE_BYTES : 0)));
                         if (ldA) tma_load_5d(sa, &tmA, bar_full + 8 * stage, kc * BLOCK_K, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, img, 0);
                         if (ldB) {
                             if (p.blockdiag) tma_load_4d(sb, &tmB, bar_full + 8 * stage, 0, 0, 0, (tap * p.coutp + nt * BLOCK_N) / 16);   // [sub-block][plane][16 rows]
@@ -315,9 +188,10 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // N-concatenated forms (NCAT): N' = 2N
             const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             const uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-            const bool split = (p.planes == 2);
-            const int sub_cols = (NCAT && split) ? 32 : 16;          // accumulator columns per 16-channel diagonal sub-block
-            const int sub_bytes = p.planes * 2048;                   // smem bytes per sub-block: [plane][16 rows][128 B]
+            const bool split = (p.planes == 2);                      // activations carry a lo plane
+            const bool wsplit = (p.wplanes == 2);                    // weights carry a lo plane
+            const int sub_cols = (NCAT && wsplit) ? 32 : 16;         // accumulator columns per 16-channel diagonal sub-block
+            const int sub_bytes = p.wplanes * 2048;                  // smem bytes per sub-block: [plane][16 rows][128 B]
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -337,7 +211,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (!(p.dbg & 16))
                         for (int s = 0; s < ntap; ++s) {
                             const uint32_t ah = sa + s * 128, al = ah + a_plane;
-                            const uint32_t bs = sb + s * p.planes * B_TILE_BYTES;
+                            const uint32_t bs = sb + s * p.wplanes * B_TILE_BYTES;
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 16; ++k) {
                                 const uint64_t a_hi = umma_desc_sw128_off(ah + k * 32, p.bo_mode), a_lo = umma_desc_sw128_off(al + k * 32, p.bo_mode);
@@ -345,14 +219,14 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     // Grouped conv: channels-per-group divides 16, so output channels [16k,16k+16) of this 64-block depend
                                     // only on input channels [16k,16k+16): one M128 x N16 x K16 product per 16-channel sub-block.
                                     // sub-block k: [plane][16 rows] of 128 B rows at K offset k*16 elements, or packed 32 B rows
-                                    const uint32_t bk = p.bdiag ? bs + k * p.planes * 512 : bs + k * sub_bytes + k * 32;
+                                    const uint32_t bk = p.bdiag ? bs + k * p.wplanes * 512 : bs + k * sub_bytes + k * 32;
                                     const uint64_t bd = p.bdiag ? umma_desc_sw32(bk) : umma_desc_sw128(bk);
                                     const uint32_t td = tmem_d + (uint32_t)(k * sub_cols);
                                     const uint32_t f0 = (kb == 0 && s == 0) ? 0u : 1u;
                                     if constexpr (NCAT) {
-                                        if (split) {
-                                            umma_bf16(td, a_hi, bd, idesc32, f0);      // [a_hi*b_hi | a_hi*b_lo]
-                                            umma_bf16(td, a_lo, bd, idesc16, 1u);      // += a_lo*b_hi
+                                        if (wsplit) {
+                                            umma_bf16(td, a_hi, bd, idesc32, f0);                 // [a_hi*b_hi | a_hi*b_lo]
+                                            if (split) umma_bf16(td, a_lo, bd, idesc16, 1u);      // += a_lo*b_hi
                                         } else {
                                             umma_bf16(td, a_hi, bd, idesc16, f0);
                                         }
@@ -360,15 +234,15 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 } else {
                                     const uint32_t first = (kb == 0 && s == 0 && k == 0) ? 0u : 1u;
                                     const uint64_t b_hi = umma_desc_sw128(bs + k * 32);
-                                    if (!split) {
+                                    if (!wsplit) {
                                         umma_bf16(tmem_d, a_hi, b_hi, idesc, first);
                                     } else if constexpr (NCAT) {
                                         umma_bf16(tmem_d, a_hi, b_hi, idesc_cat, first);                // [a_hi*b_hi | a_hi*b_lo]
-                                        umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);                       // += a_lo*b_hi
+                                        if (split) umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);            // += a_lo*b_hi
                                     } else {
                                         const uint64_t b_lo = umma_desc_sw128(bs + B_TILE_BYTES + k * 32);
-                                        umma_bf16(tmem_d, a_lo, b_hi, idesc, first);
-                                        umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                                        umma_bf16(tmem_d, a_hi, b_lo, idesc, first);
+                                        if (split) umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
                                         umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
                                     }
                                 }
@@ -399,7 +273,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // value is main + aux: dense = columns c and BLOCK_N + c, block-diagonal = per 16-channel sub-block [main16 | aux16].
         auto ld_acc = [&](int col0, uint32_t* raw) {
             const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-            if (NCAT && p.planes == 2) {
+            if (NCAT && p.wplanes == 2) {
                 uint32_t y[CHUNK];
                 if constexpr (CHUNK == 32) {
                     if (p.blockdiag) {
@@ -682,28 +556,13 @@ struct TcEnv {
 };
 const TcEnv& tc_env() { static const TcEnv e; return e; }
 
-typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_tmEncodeTiled get_encode() {
-    static PFN_tmEncodeTiled fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = (PFN_tmEncodeTiled)f;
-    }
-    return fn;
-}
-
 template <int BLOCK_N, int STAGES, int STG>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const TcP& p_in, cudaStream_t st) {
     TcP p = p_in;
     p.res_tma = ((STG == 3 || (STG == 2 && BLOCK_N == 64 && STAGES == 2)) && p.tma_out && p.res_split && p_in.res_tma) ? 1 : 0;
     const size_t b_tile = p.bdiag ? (size_t)(BLOCK_N / 16) * 512 : (size_t)BLOCK_N * BLOCK_K * 2;
-    size_t stage_bytes = (size_t)p.planes * (A_TILE_BYTES + b_tile);
-    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.planes * 3 * b_tile;
+    size_t stage_bytes = (size_t)p.planes * A_TILE_BYTES + (size_t)p.wplanes * b_tile;
+    if (p.halo) stage_bytes = (((size_t)p.planes * (p.TW + 2) * 128 + 1023) & ~(size_t)1023) + (size_t)p.wplanes * 3 * b_tile;
     size_t smem = (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static size_t attr_set[HEAL_MAX_DEVICES] = {};
@@ -730,13 +589,15 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
 
 extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
                               const void* w_packed, const void* w_diag, int w_rows, int coutp, const float* bias,
-                              int kh, int kw, int stride, int pad, int blockdiag, int planes,
+                              int kh, int kw, int stride, int pad, int blockdiag, int planes, int w_planes,
                               const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                               void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
                               float* out_f32, int out32_cstride, int out32_coffset,
                               int Ho, int Wo, int Cout, int upsample, int relu, void* stream_) {
     if (!in_split || !w_packed || (!out_split && !out_f32)) return HEAL_ERR_ARG;
     if (planes != 1 && planes != 2) return HEAL_ERR_ARG;
+    if (w_planes != 1 && w_planes != 2) return HEAL_ERR_ARG;
+    if (planes == 2 && w_planes != 2) return HEAL_ERR_UNSUPPORTED;
     if ((Cin % BLOCK_K) || (in_cstride & 7) || (in_coffset & 7) || upsample < 1) return HEAL_ERR_UNSUPPORTED;
     if (stride < 1 || stride > 2) return HEAL_ERR_UNSUPPORTED;
     if (Ho != (H + 2 * pad - kh) / stride + 1 || Wo != (W + 2 * pad - kw) / stride + 1) return HEAL_ERR_ARG;
@@ -760,7 +621,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     p.n_tiles = w_rows / taps / block_n;
     p.stride = stride; p.blockdiag = blockdiag;
     if (upsample > 1) p.n_tiles = w_rows / block_n;
-    p.planes = planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
+    p.planes = planes; p.wplanes = w_planes; p.coutp = coutp; p.relu = relu; p.up = upsample; p.bias = bias;
     const TcEnv& env = tc_env();
     p.dbg = env.dbg; p.pdl = env.pdl;
     p.res_split = (const __nv_bfloat16*)res_split; p.res_plane = res_plane_stride; p.res_f32 = res_f32;
@@ -792,7 +653,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         // hi and lo planes of the same rows must be adjacent for the N-concatenated MMAs (see NCAT in the kernel).
         const cuuint64_t wk = blockdiag ? 64 : Cin;      // K extent of the packed weight matrix
         const cuuint64_t row_b = wk * 2, plane_b = (cuuint64_t)w_rows * wk * 2;
-        const cuuint32_t pl = (cuuint32_t)planes;
+        const cuuint32_t pl = (cuuint32_t)w_planes;
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r;
         p.bdiag = (blockdiag && w_diag) ? 1 : 0;
@@ -800,38 +661,38 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             // packed diagonal sub-blocks in global memory: [plane][taps * coutp rows][16] bf16 (32 B rows) -> a quarter of the bytes
             const cuuint64_t pb = (cuuint64_t)w_rows * 32;
             if (p.halo) {                   // smem [3 taps][4 sub-blocks][plane][16 rows][32 B]
-                cuuint64_t d[5] = {16, 16, (cuuint64_t)planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
+                cuuint64_t d[5] = {16, 16, (cuuint64_t)w_planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
                 cuuint64_t st[4] = {32, pb, 512, (cuuint64_t)coutp * 32};
                 cuuint32_t b[5] = {16u, 16u, pl, (cuuint32_t)block_n / 16, 3u};
                 r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)w_diag, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             } else {                        // smem [4 sub-blocks][plane][16 rows][32 B]
-                cuuint64_t d[4] = {16, 16, (cuuint64_t)planes, (cuuint64_t)w_rows / 16};
+                cuuint64_t d[4] = {16, 16, (cuuint64_t)w_planes, (cuuint64_t)w_rows / 16};
                 cuuint64_t st[3] = {32, pb, 512};
                 cuuint32_t b[4] = {16u, 16u, pl, (cuuint32_t)block_n / 16};
                 r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_diag, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             }
         } else if (blockdiag && p.halo) {   // smem [3 taps][4 sub-blocks][plane][16 rows]
-            cuuint64_t d[5] = {wk, 16, (cuuint64_t)planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
+            cuuint64_t d[5] = {wk, 16, (cuuint64_t)w_planes, (cuuint64_t)coutp / 16, (cuuint64_t)taps};
             cuuint64_t st[4] = {row_b, plane_b, 16 * row_b, (cuuint64_t)coutp * row_b};
             cuuint32_t b[5] = {(cuuint32_t)BLOCK_K, 16u, pl, (cuuint32_t)block_n / 16, 3u};
             r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else if (blockdiag) {             // smem [4 sub-blocks][plane][16 rows]
-            cuuint64_t d[4] = {wk, 16, (cuuint64_t)planes, (cuuint64_t)w_rows / 16};
+            cuuint64_t d[4] = {wk, 16, (cuuint64_t)w_planes, (cuuint64_t)w_rows / 16};
             cuuint64_t st[3] = {row_b, plane_b, 16 * row_b};
             cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, 16u, pl, (cuuint32_t)block_n / 16};
             r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else if (p.halo) {                // smem [3 taps][plane][block_n rows]: one box brings the 3 horizontal taps of a kernel row
-            cuuint64_t d[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)planes, (cuuint64_t)taps};
+            cuuint64_t d[4] = {wk, (cuuint64_t)coutp, (cuuint64_t)w_planes, (cuuint64_t)taps};
             cuuint64_t st[3] = {row_b, plane_b, (cuuint64_t)coutp * row_b};
             cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, pl, 3u};
             r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {                            // smem [plane][block_n rows]
-            cuuint64_t d[3] = {wk, (cuuint64_t)w_rows, (cuuint64_t)planes};
+            cuuint64_t d[3] = {wk, (cuuint64_t)w_rows, (cuuint64_t)w_planes};
             cuuint64_t st[2] = {row_b, plane_b};
             cuuint32_t b[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n, pl};
             r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w_packed, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -34,9 +34,14 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     if (threadIdx.x < PV_COUT) sB[threadIdx.x] = bf[threadIdx.x];
     __syncthreads();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int v = blockIdx.x * PV_WARPS + warp;
     int Mdev = num_voxels_dev ? min(M, num_voxels_dev[0]) : M;
-    if (v >= Mdev) return;
+    // ---- lane = channel pair: this lane's two weight columns stay in registers for every pillar the warp processes ----
+    float w0[PV_CIN], w1[PV_CIN];
+#pragma unroll
+    for (int k = 0; k < PV_CIN; ++k) { w0[k] = sW[k * PV_COUT + 2 * lane]; w1[k] = sW[k * PV_COUT + 2 * lane + 1]; }
+    const float b0 = sB[2 * lane], b1 = sB[2 * lane + 1];
+    // persistent warps: grid sized for the machine (the live pillar count is on the device, ~5x below the row capacity)
+    for (int v = blockIdx.x * PV_WARPS + warp; v < Mdev; v += gridDim.x * PV_WARPS) {
 
     // ---- stage A: lane = point slot --------------------------------------------------------
     int n = num_points[v];
@@ -58,10 +63,6 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     __syncwarp();
 
     // ---- stage B: lane = channel pair ------------------------------------------------------
-    float w0[PV_CIN], w1[PV_CIN];
-#pragma unroll
-    for (int k = 0; k < PV_CIN; ++k) { w0[k] = sW[k * PV_COUT + 2 * lane]; w1[k] = sW[k * PV_COUT + 2 * lane + 1]; }
-    float b0 = sB[2 * lane], b1 = sB[2 * lane + 1];
     float m0 = 0.f, m1 = 0.f;  // ReLU output >= 0, so 0 is the identity of the running max
     // padded slots are all-zero rows: Linear gives +0, so each contributes exactly ReLU(b) to the max -- fold them into one
     // fmaxf instead of T - n dead dot products (LiDAR pillars hold ~3 points of T = 32)
@@ -92,6 +93,8 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
                 reinterpret_cast<__nv_bfloat162*>(b + canvas.plane)[lane] = __floats2bfloat162_rn(o.x - hf.x, o.y - hf.y);
             }
         }
+    }
+    __syncwarp();          // sF[warp] is rewritten by the next pillar
     }
 }
 
@@ -142,6 +145,7 @@ extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* v
         cv.plane = canvas_out->plane_stride;
     }
     int grid = (num_voxels + PV_WARPS - 1) / PV_WARPS;
+    if (grid > HEAL_NUM_SMS * 8) grid = HEAL_NUM_SMS * 8;
     k_pillar_vfe_scatter<<<grid, PV_WARPS * 32, 0, (cudaStream_t)stream_>>>(
         (const float4*)voxel_features, voxel_num_points, (const int4*)voxel_coords, num_voxels_dev, num_voxels,
         w_folded, b_folded, c, pillar_features_out, cv);

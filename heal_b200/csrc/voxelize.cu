@@ -191,9 +191,12 @@ __global__ void k_select(const float4* __restrict__ pts, const int* __restrict__
                          const int* __restrict__ seg_local, const int* __restrict__ seg_blockoff,
                          const int* __restrict__ num_voxels, int T,
                          float4* __restrict__ voxels, int* __restrict__ num_points) {
-    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (v >= num_voxels[0]) return;
+    // persistent warps: the launch is sized for the machine, not for the row CAPACITY (the live voxel count is on the device
+    // and typically 4-5x below the capacity: a capacity-sized grid spent most of its blocks on an early exit)
+    const int lane = threadIdx.x & 31;
+    const int nv = num_voxels[0];
+    const int wstride = (gridDim.x * blockDim.x) >> 5;
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += wstride) {
     int n = cnt[v];
     int base = seg_local[v] + seg_blockoff[v / SCAN_BLOCK];
     int m = min(n, T);
@@ -224,6 +227,7 @@ __global__ void k_select(const float4* __restrict__ pts, const int* __restrict__
         }
     }
     if (lane == 0) num_points[v] = m;
+    }
 }
 
 __global__ void k_mean_vfe(const float4* __restrict__ voxels, const int* __restrict__ num_points, int M, int T,
@@ -322,6 +326,7 @@ extern "C" int heal_voxelize(const float* points, const int* agent_offsets, int 
     k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(seg_blockoff, nb_c);
     k_fill<<<gp, TB, 0, st>>>(pt_vid, P, seg_local, seg_blockoff, cursor, seg);
     int gv = (int)(((size_t)capacity * 32 + TB - 1) / TB);
+    if (gv > HEAL_NUM_SMS * 8) gv = HEAL_NUM_SMS * 8;           // 8 resident blocks of 8 warps per SM, warp-stride loop over the voxels
     k_select<<<gv, TB, 0, st>>>((const float4*)points, seg, cnt, seg_local, seg_blockoff, num_voxels_out,
                                 c.T, (float4*)voxels_out, num_points_out);
     return heal_check_launch(10);

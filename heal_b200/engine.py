@@ -9,7 +9,9 @@ changes (load_state_dict / optimizer step) or the module moves device.
 Precision modes (set_precision):
   'tc32'  (default) dense stride-1 convs on tcgen05 with split-bf16 operands (3 MMAs / K-step, fp32
           accumulate: fp32-equivalent, meets the 1e-3 parity bar); activations stored as split-bf16.
-  'bf16'  same kernels with a single bf16 plane (1e-2 parity bar, BASELINE config 4).
+  'bf16'  same kernels, activations stored as ONE bf16 plane, weights keep both planes (a_hi x [b_hi | b_lo]: the weights are
+          not rounded to 8 mantissa bits, only the activations are; 1e-2 parity bar, BASELINE config 4).  HEAL_BF16_WEIGHTS=1
+          rounds the weights too (plain bf16 x bf16, for A/B measurements).
   'fp32'  everything on the fp32 CUDA-core kernels with fp32 storage (exact-fp32 cross-check path).
 """
 from __future__ import annotations
@@ -29,6 +31,7 @@ SPARSE_STEM = True     # PointPillars: feed the first stride-2 residual block fr
 # occupancy (0.22 vs 0.20 ms: a 16-pixel row block has 1-2 hit rows per tap, so ~90 % of each MMA multiplies zeros) -> opt-in.
 import os as _os
 STEM_TC = _os.environ.get("HEAL_STEM_TC", "0") == "1"
+BF16_WEIGHTS = _os.environ.get("HEAL_BF16_WEIGHTS", "0") == "1"
 
 
 def set_precision(mode: str):
@@ -94,7 +97,7 @@ def conv_bn_act(x: Act, conv, bn=None, relu=False, residual: Optional[Act] = Non
             x = ops.convert(x, fmt)
         if residual is not None and residual.fmt not in ("f32", fmt):
             residual = ops.convert(residual, fmt)
-        pc = packed(conv, bn, relu, extra_pad, kind="tc2" if PRECISION == "tc32" else "tc1")
+        pc = packed(conv, bn, relu, extra_pad, kind="tc1" if (PRECISION == "bf16" and BF16_WEIGHTS) else "tc2")
         if out_fmt == "f32":
             _, o32 = ops.conv2d_tc(x, pc, residual=residual, want_split=False, out_f32=out, want_f32=True,
                                    out32_coffset=out_coffset)

@@ -53,6 +53,20 @@ def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stri
 
 
 _FOLD = {}
+_FOLD_TC = {}
+TC_SHAPES = {(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128)}     # instantiations of heal_spconv_gather_gemm_tc
+
+
+def folded_tc(conv, bn):
+    """Packed split-bf16 weights for the tensor-core gather-GEMM (ops.pack_spconv_tc), cached like `folded`."""
+    sig = _sig(conv, bn)
+    hit = _FOLD_TC.get(id(conv))
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    wp, _ = folded(conv, bn)
+    pk = ops.pack_spconv_tc(wp)
+    _FOLD_TC[id(conv)] = (sig, pk)
+    return pk
 
 
 def folded(conv, bn):
@@ -102,16 +116,25 @@ class VoxelBackBone8x(nn.Module):
         self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 64}
 
     @staticmethod
-    def _run(st, conv, bn, cache):
-        """one conv+BN+ReLU; returns the output SparseTensor (with feats)"""
+    def _run(st, conv, bn, cache, want_f32=False):
+        """one conv+BN+ReLU; returns the output SparseTensor (with feats).  Features are fp32 rows (cap, C) on the CUDA-core
+        path and split-bf16 rows (cap, 2C) on the tensor-core path (every layer with >= 16 input channels unless the engine is
+        in 'fp32' mode; conv_input's 4 input channels = K of 4 per offset stay on the fp32 kernel: 0.3 % of the FLOPs)."""
+        from ... import engine
         w, b = folded(conv, bn)
         if conv.subm:
             key = conv.indice_key
             if key not in cache:
                 cache[key] = ops.sp_subm_neighbors(st, conv.kernel_size)
-            nbr = cache[key]
-            return st.with_feats(ops.sp_gather_gemm(st.feats, nbr, st.rows_dev, w, b, True))
-        out, nbr = ops.sp_strided(st, conv.kernel_size, conv.stride, conv.padding)
+            nbr, out = cache[key], st
+        else:
+            out, nbr = ops.sp_strided(st, conv.kernel_size, conv.stride, conv.padding)
+            cache.setdefault("_strided", []).append(out)
+        cin, cout = conv.in_channels, conv.out_channels
+        if engine.PRECISION != "fp32" and (cin, cout) in TC_SHAPES:
+            fin = st.feats if st.feats.dtype == torch.bfloat16 else ops.rows_to_split(st.feats, st.rows_dev)
+            return out.with_feats(ops.sp_gather_gemm_tc(fin, nbr, out.rows_dev, folded_tc(conv, bn), b, True, cin, cout, want_f32=want_f32))
+        assert st.feats.dtype == torch.float32, "fp32 gather-GEMM after a tensor-core layer is not a configured path"
         return out.with_feats(ops.sp_gather_gemm(st.feats, nbr, out.rows_dev, w, b, True))
 
     def forward_sparse(self, feats, coords, batch_size, rows_dev=None):
@@ -126,7 +149,9 @@ class VoxelBackBone8x(nn.Module):
             for blk in seq:
                 x = self._run(x, blk[0], blk[1], cache)
             levels.append(x)
-        out = self._run(x, self.conv_out[0], self.conv_out[1], cache)
+        out = self._run(x, self.conv_out[0], self.conv_out[1], cache, want_f32=True)
+        if not torch.cuda.is_current_stream_capturing():
+            ops.sp_check_overflow(cache.get("_strided", []))     # the encoder's only host sync (none inside a captured frame)
         return out, levels
 
     def forward(self, batch_dict):

@@ -521,7 +521,7 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
               out_f32: Optional[Act] = None, want_f32: bool = False, out32_coffset: int = 0):
     """tcgen05 conv.  x: Act 'split' (planes 2) or 'bf16' (planes 1).  Returns (Act split/bf16 | None, Act f32 | None)."""
     _need_cuda(pc.w)
-    assert x.planes == pc.planes and x.planes in (1, 2)
+    assert x.planes in (1, 2) and pc.planes >= x.planes      # weights may carry a lo plane the activations do not ('bf16' mode)
     N, H, W = x.N, x.H, x.W
     up = pc.up
     Ho, Wo = (H + 2 * pc.pad - pc.kh) // pc.stride + 1, (W + 2 * pc.pad - pc.kw) // pc.stride + 1
@@ -535,11 +535,11 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
         if residual.fmt == "f32":
             res_f32, res_cs = residual.t, residual.cstride
         else:
-            assert residual.planes == pc.planes
+            assert residual.planes == x.planes
             res_split, res_cs, res_plane = residual.t, residual.cstride, residual.plane_stride
     fam = f"conv_tc{pc.kh}x{pc.kw}" + ("_deconv" if up > 1 else "") + ("_grouped" if pc.blockdiag else "") + (f"_s{pc.stride}" if pc.stride > 1 else "")
     flops = 2.0 * N * Ho * Wo * pc.cout * (pc.cin // pc.groups) * pc.kh * pc.kw * up * up
-    epb = 2.0 * pc.planes
+    epb = 2.0 * x.planes
     nbytes = N * H * W * pc.cin * epb + (pc.w_diag if pc.w_diag is not None else pc.w).numel() * 2.0 \
         + (N * Ho * Wo * up * up * pc.cout * epb if out is not None else 0) \
         + (N * Ho * Wo * up * up * pc.cout * 4.0 if out_f32 is not None else 0) \
@@ -547,7 +547,7 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
     with _Prof(fam, flops, nbytes):
         rc = lib.heal_conv2d_tc(_p(x.t), x.plane_stride, N, H, W, pc.cin, x.cstride, in_coffset,
                                 _p(pc.w), _p(pc.w_diag), pc.w.shape[1], pc.coutp, _p(pc.bias), pc.kh, pc.kw, pc.stride, pc.pad,
-                                1 if pc.blockdiag else 0, pc.planes,
+                                1 if pc.blockdiag else 0, x.planes, pc.planes,
                                 _p(res_split), res_plane, _p(res_f32), res_cs, 0,
                                 _p(out.t) if out is not None else _vp(0), out.plane_stride if out is not None else 0,
                                 out.cstride if out is not None else 0, out_coffset,
@@ -690,15 +690,23 @@ def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
     return nbr
 
 
+SP_GROWTH = 1.5     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
+
+
 def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int] = None):
-    """SparseConv3d rulebook: returns (output SparseTensor without feats, nbr (out_cap, K))."""
+    """SparseConv3d rulebook: returns (output SparseTensor without feats, nbr (out_cap, K)).  No host sync: the live output
+    row count stays on the device (`rows_dev`; rows beyond `out_capacity` are dropped by the kernels and show up as
+    rows_dev > capacity, which `sp_check_overflow` reports).  Default capacity = SP_GROWTH x the input capacity, bounded by
+    the exact worst case (fan-out x inputs, number of cells): a stride-2 3x3x3 conv dilates LiDAR surfaces by ~1.3x at the
+    0.1 m level and shrinks them afterwards, and the voxeliser's own capacity already carries ~1.6x headroom."""
     oshape = [(st.spatial_shape[i] + 2 * pad[i] - ksize[i]) // stride[i] + 1 for i in range(3)]
     K = int(ksize[0] * ksize[1] * ksize[2])
     if out_capacity is None:
         fan = 1
         for i in range(3):
             fan *= -(-ksize[i] // stride[i])
-        out_capacity = int(min(st.capacity * fan, st.batch * oshape[0] * oshape[1] * oshape[2]))
+        out_capacity = int(min(st.capacity * fan, st.batch * oshape[0] * oshape[1] * oshape[2],
+                               max(int(st.capacity * SP_GROWTH), 1024)))
     dev = st.coords.device
     ts = lib.heal_spconv_table_size(out_capacity)
     okeys = torch.empty((ts,), dtype=torch.int32, device=dev)
@@ -713,9 +721,19 @@ def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int]
                                               _host_i32(ksize), _host_i32(stride), _host_i32(pad), out_capacity,
                                               _p(ocoords), _p(orows), _p(okeys), _p(ovals), _p(nbr), _p(ws), ws.numel(), _stream())
     check(rc, "heal_spconv_strided_rulebook")
-    # one host sync per strided layer (spconv does the same) so that worst-case capacities do not compound level to level
-    m = min(int(orows.item()), out_capacity)
-    return SparseTensor(None, ocoords[:m], None, oshape, st.batch, (okeys, ovals), table_capacity=out_capacity), nbr[:m]
+    return SparseTensor(None, ocoords, orows, oshape, st.batch, (okeys, ovals), table_capacity=out_capacity), nbr
+
+
+def sp_check_overflow(tensors) -> None:
+    """ONE host sync for a whole encoder: raises if any strided conv produced more rows than its capacity."""
+    live = [t for t in tensors if t.rows_dev is not None]
+    if not live:
+        return
+    counts = torch.cat([t.rows_dev[:1] for t in live]).tolist()
+    for t, n in zip(live, counts):
+        if n > t.capacity:
+            raise RuntimeError(f"sparse conv output rows {n} exceed the capacity {t.capacity} (spatial shape {t.spatial_shape}); "
+                               "raise heal_b200.ops.SP_GROWTH or pass out_capacity")
 
 
 def sp_gather_gemm(feats: torch.Tensor, nbr: torch.Tensor, rows_dev, weight: torch.Tensor, bias, relu: bool) -> torch.Tensor:
@@ -733,6 +751,51 @@ def sp_gather_gemm(feats: torch.Tensor, nbr: torch.Tensor, rows_dev, weight: tor
         rc = lib.heal_spconv_gather_gemm(_p(feats), _p(nbr), _p(rows_dev), cap, K, _p(weight), _p(bias), cin, cout,
                                          1 if relu else 0, _p(out), _stream())
     check(rc, "heal_spconv_gather_gemm")
+    return out
+
+
+def pack_spconv_tc(wp: torch.Tensor) -> torch.Tensor:
+    """Folded sparse-conv weights (K, Cin, Cout) fp32 -> [2 planes][KB*Cout rows][64] bf16 for heal_spconv_gather_gemm_tc:
+    K-block kb holds the 64/Cin kernel offsets kb*TPK .. kb*TPK+TPK-1 side by side along K (zero columns for padding offsets)."""
+    K, cin, cout = wp.shape
+    assert cin in (16, 32, 64)
+    tpk = 64 // cin
+    kb = -(-K // tpk)
+    rows = torch.zeros((kb, cout, 64), dtype=torch.float32)
+    w = wp.detach().float().cpu()
+    for k in range(K):
+        b, tl = divmod(k, tpk)
+        rows[b, :, tl * cin:(tl + 1) * cin] = w[k].t()
+    return split_bf16(rows.reshape(kb * cout, 64), 2).to(wp.device)
+
+
+def rows_to_split(feats: torch.Tensor, rows_dev) -> torch.Tensor:
+    """(cap, C) fp32 rows -> (cap, 2C) bf16 split rows [hi | lo]."""
+    cap, C = feats.shape
+    out = torch.empty((cap, 2 * C), dtype=torch.bfloat16, device=feats.device)
+    with _Prof("rows_to_split", 0, cap * C * 8.0):
+        rc = lib.heal_rows_to_split(_p(feats), _p(rows_dev), cap, C, _p(out), _stream())
+    check(rc, "heal_rows_to_split")
+    return out
+
+
+def sp_gather_gemm_tc(feats_split: torch.Tensor, nbr: torch.Tensor, rows_dev, w_packed: torch.Tensor, bias, relu: bool,
+                      cin: int, cout: int, want_f32: bool = False) -> torch.Tensor:
+    """feats_split (Min, 2*Cin) bf16 split rows; nbr (cap,K) i32 -> (cap, 2*Cout) bf16 split rows, or (cap, Cout) fp32."""
+    _need_cuda(feats_split, nbr, w_packed)
+    cap, K = nbr.shape
+    assert feats_split.dtype == torch.bfloat16 and feats_split.shape[1] == 2 * cin and feats_split.is_contiguous()
+    dev = feats_split.device
+    out = torch.empty((cap, cout), dtype=torch.float32, device=dev) if want_f32 else torch.empty((cap, 2 * cout), dtype=torch.bfloat16, device=dev)
+
+    def _pairs():
+        m = cap if rows_dev is None else min(cap, int(rows_dev[0].item()))
+        return float((nbr[:m] >= 0).sum().item()), float(m)
+    with _Prof("spconv_gather_gemm_tc", lambda: 2.0 * _pairs()[0] * cin * cout,
+               lambda: _pairs()[0] * (cin * 4.0 + 4.0) + _pairs()[1] * (cout * 4.0 + K * 4.0)):
+        rc = lib.heal_spconv_gather_gemm_tc(_p(feats_split), _p(nbr), _p(rows_dev), cap, K, _p(w_packed), _p(bias), cin, cout,
+                                            1 if relu else 0, _vp(0) if want_f32 else _p(out), _p(out) if want_f32 else _vp(0), _stream())
+    check(rc, "heal_spconv_gather_gemm_tc")
     return out
 
 
@@ -899,6 +962,6 @@ def _guard(fn):
 
 
 for _name in ("convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
-              "lss_cell_index", "lss_pool", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sparse_to_bev",
+              "lss_cell_index", "lss_pool", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
               "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
     globals()[_name] = _guard(globals()[_name])

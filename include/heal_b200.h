@@ -137,9 +137,11 @@ int heal_conv2d_simt(const heal_act_t* in, int N, int H, int W, int Cin,
  *              w_diag (optional, NULL otherwise): the same weights as [planes][kh*kw][coutp][16] — only the 16x16 diagonal
  *              sub-block of each output channel; when given, the kernel streams these (a quarter of the bytes, 32 B-swizzled
  *              TMA boxes) instead of the 64-wide rows of w_packed */
+/* planes / w_planes of heal_conv2d_tc: activation planes (1 = bf16, 2 = split-bf16) and weight planes. (2,2) = fp32-equivalent
+ * "tc32"; (1,2) = the "bf16" engine mode: bf16 activations x split (un-rounded) weights, a_hi x [b_hi | b_lo]; (1,1) = plain bf16. */
 int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int N, int H, int W, int Cin, int in_cstride, int in_coffset,
                    const void* w_packed, const void* w_diag, int w_rows, int coutp, const float* bias,
-                   int kh, int kw, int stride, int pad, int blockdiag, int planes,
+                   int kh, int kw, int stride, int pad, int blockdiag, int planes, int w_planes,
                    const void* res_split, size_t res_plane_stride, const float* res_f32, int res_cstride, int res_coffset,
                    void* out_split, size_t out_plane_stride, int out_cstride, int out_coffset,
                    float* out_f32, int out32_cstride, int out32_coffset,
@@ -212,6 +214,17 @@ int heal_spconv_strided_rulebook(const int* in_coords, const int* in_rows_dev, i
 int heal_spconv_gather_gemm(const float* in_feats, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,
                             const float* weight, const float* bias, int c_in, int c_out, int relu,
                             float* out_feats, void* stream);
+
+/* The same gather-GEMM on the tensor cores (csrc/spconv_tc.cu: tcgen05.mma, TMEM accumulators, cp.async row gather into
+ * 128B-swizzled K-major tiles, TMA weight tiles), for c_in in {16,32,64}.  Features are "split rows": (rows, 2*C) bf16 =
+ * [hi C | lo C] with x ~= hi + lo; products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation (fp32-equivalent).
+ *   w_packed   [2 planes][KB * c_out rows][64] bf16, KB = ceil(kvol / (64 / c_in)); column = (offset within K-block) * c_in + ci
+ *   out_split_rows (capacity, 2*c_out) bf16 and / or out_f32 (capacity, c_out) */
+int heal_spconv_gather_gemm_tc(const void* in_split_rows, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,
+                               const void* w_packed, const float* bias, int c_in, int c_out, int relu,
+                               void* out_split_rows, float* out_f32, void* stream);
+/* fp32 rows (capacity, C) -> split rows (capacity, 2*C) bf16 */
+int heal_rows_to_split(const float* rows_f32, const int* rows_dev, int capacity, int channels, void* out_split_rows, void* stream);
 int heal_sparse_to_bev(const float* feats, const int* coords, const int* rows_dev, int capacity, int C, int D, int H, int W,
                        float* bev_out, void* stream);
 

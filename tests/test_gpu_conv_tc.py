@@ -52,12 +52,13 @@ def _mk(case):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("planes", [2, 1])
-def test_conv_tc(case, planes):
+@pytest.mark.parametrize("planes,wplanes", [(2, 2), (1, 2), (1, 1)], ids=["tc32", "bf16act_splitw", "bf16"])
+def test_conv_tc(case, planes, wplanes):
+    """(activation planes, weight planes): (2,2) fp32-equivalent; (1,2) the engine's 'bf16' mode; (1,1) plain bf16 x bf16."""
     from heal_b200 import ops
     name, N, Cin, H, W, Cout, k, pad, bias, bn, relu, res = case
     conv, bnm, x, r, y = _mk(case)
-    pc = ops.pack_conv_tc(conv, bnm, relu, planes=planes).to("cuda")
+    pc = ops.pack_conv_tc(conv, bnm, relu, planes=wplanes).to("cuda")
     fmt = "split" if planes == 2 else "bf16"
     xs = ops.convert(ops.to_act(x.cuda()), fmt)
     rr = None
@@ -72,9 +73,12 @@ def test_conv_tc(case, planes):
     scale = y.abs().max().item()
     e32 = (got32 - y).abs().max().item()
     es = (gots - y).abs().max().item()
-    print(f"{name} planes={planes}: max|y|={scale:.3f} err_f32out={e32:.3e} err_splitout={es:.3e}")
-    tol = 1e-3 if planes == 2 else 3e-2 * max(scale, 1.0)
-    assert e32 < tol and es < (tol if planes == 2 else tol + 1e-2 * max(scale, 1.0))
+    print(f"{name} planes={planes}/{wplanes}: max|y|={scale:.3f} err_f32out={e32:.3e} err_splitout={es:.3e}")
+    if planes == 2:
+        assert e32 < 1e-3 and es < 1e-3
+    else:       # bf16 activations: north_star's 1e-2 (relative to the tensor scale) for one layer; the bf16 OUTPUT adds its own rounding
+        tol = (1e-2 if wplanes == 2 else 1.5e-2) * max(scale, 1.0)
+        assert e32 < tol and es < tol + 4e-3 * max(scale, 1.0)
 
 
 @pytest.mark.parametrize("up", [1, 2, 4])

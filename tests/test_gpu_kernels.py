@@ -228,8 +228,8 @@ def test_warp_att_golden(golden_dir):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tc32", "tc32-mma"])
-def test_sparse_stem_equals_dense_canvas_path(prec):
-    """scatter + first residual block straight from the pillar list == the same block on the materialised canvas."""
+def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
+    """scatter + first residual block straight from the pillar list == the same block on the materialised canvas == the oracle."""
     from heal_b200 import ops, synth, engine
     from heal_b200.models.sub_modules.resblock import BasicBlock, conv1x1
     from oracle import procedural
@@ -247,7 +247,8 @@ def test_sparse_stem_equals_dense_canvas_path(prec):
         w, b = ops.fold_linear_bn(sd["vfe.pfn_layers.0.linear.weight"], sd["vfe.pfn_layers.0.norm.weight"], sd["vfe.pfn_layers.0.norm.bias"],
                                   sd["vfe.pfn_layers.0.norm.running_mean"], sd["vfe.pfn_layers.0.norm.running_var"], 1e-3)
         blk = BasicBlock(64, 64, 2, torch.nn.Sequential(conv1x1(64, 64, 2), torch.nn.BatchNorm2d(64))).eval()
-        blk.load_state_dict(procedural.make_state_dict(procedural.shapes_of(blk)), strict=True)
+        blk_sd = procedural.make_state_dict(procedural.shapes_of(blk))
+        blk.load_state_dict(blk_sd, strict=True)
         blk = blk.cuda()
         args = (col["voxel_features"], col["voxel_num_points"], col["voxel_coords"], w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2)
         sparse = ops.pillar_vfe_sparse(*args)
@@ -264,6 +265,14 @@ def test_sparse_stem_equals_dense_canvas_path(prec):
         tol = (1e-5 if prec == "fp32" else 1e-4) * max(scale, 1.0)
         err = (a - d).abs().max().item()
         assert err < tol, (err, tol, scale)
+        # ... and against the ORACLE (PillarVFE -> scatter -> BasicBlock on CPU, oracle/nets.py), not only against our own dense path
+        from oracle import nets
+        cpu = {k: v.cpu() for k, v in col.items()}
+        with torch.no_grad():
+            pf = nets.pillar_vfe(sd, "vfe", cpu["voxel_features"], cpu["voxel_num_points"], cpu["voxel_coords"], PP_VOXEL, PP_RANGE)
+            ref = nets.basic_block(nets.scatter(pf, cpu["voxel_coords"], 512, 512), {"blk." + k: v for k, v in blk_sd.items()}, "blk", 2, True)
+        err_o = (a - ref).abs().max().item()
+        assert err_o < 1e-3 * max(ref.abs().max().item(), 1.0), (err_o, ref.abs().max().item())
     finally:
         engine.SPARSE_STEM = True
         engine.STEM_TC = old_tc

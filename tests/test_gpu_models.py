@@ -34,8 +34,8 @@ def _tol_check(got, ref, tol, name):
     err = (got - ref).abs().max().item()
     scale = max(ref.abs().max().item(), 1.0)
     print(f"{name}: max|ref|={scale:.3f} max_abs_err={err:.3e}")
-    if tol is None:      # bf16 mode: 1e-2-class relative to the tensor scale, through ~70 layers
-        assert err < 5e-2 * scale, (name, err, scale)
+    if tol is None:      # bf16 mode: north_star's 1e-2, relative to the tensor scale, through ~70 layers
+        assert err < 1e-2 * scale, (name, err, scale)
     else:
         assert err < tol * scale, (name, err, scale)
 

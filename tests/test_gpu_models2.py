@@ -18,7 +18,7 @@ def _tol_check(got, ref, tol, name):
     err = (got - ref).abs().max().item()
     scale = max(ref.abs().max().item(), 1.0)
     print(f"{name}: max|ref|={scale:.3f} max_abs_err={err:.3e}")
-    assert err < (5e-2 if tol is None else tol) * scale, (name, err, scale)
+    assert err < (1e-2 if tol is None else tol) * scale, (name, err, scale)
 
 
 @pytest.fixture(autouse=True)

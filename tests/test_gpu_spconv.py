@@ -53,8 +53,8 @@ def test_strided_conv_vs_oracle(ksize, stride, pad, shape):
     st = ops.SparseTensor(feats.cuda(), torch.from_numpy(coords).cuda(), None, shape, B)
     out_st, nbr = ops.sp_strided(st, ksize, stride, pad)
     assert out_st.spatial_shape == oshape
-    m = out_st.capacity
-    assert m == len(rc)                                           # same active output set size
+    m = int(out_st.rows_dev.item())                               # live rows stay on the device (no host sync inside sp_strided)
+    assert m == len(rc) and m <= out_st.capacity                  # same active output set size
     wp = w.reshape(cout, K, cin).permute(1, 2, 0).contiguous().cuda()
     out = ops.sp_gather_gemm(st.feats, nbr, None, wp, None, False)[:m].cpu()
     oc = out_st.coords[:m].cpu().numpy()
@@ -67,6 +67,63 @@ def test_strided_conv_vs_oracle(ksize, stride, pad, shape):
     # the site -> row table of the new level serves SubM lookups: every output site finds itself at the centre offset
     nb2 = ops.sp_subm_neighbors(out_st, (3, 3, 3))
     assert torch.equal(nb2[:m, 13].cpu(), torch.arange(m, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("cin,cout,n", [(16, 16, 777), (16, 32, 5000), (32, 32, 3000), (32, 64, 4100), (64, 64, 2000), (64, 128, 1500)])
+def test_subm_conv_tensor_core_vs_oracle(cin, cout, n):
+    """heal_spconv_gather_gemm_tc (tcgen05, split-bf16 rows, cp.async gather) vs the oracle: fp32-equivalent (2^-16 per product)."""
+    from heal_b200 import ops
+    rng = np.random.default_rng(100 + cin + cout)
+    shape, B = [21, 64, 64], 2
+    feats, coords = _random_sparse(rng, B, shape, n, cin)
+    w = torch.from_numpy((rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    ref = torch.relu(sc.subm_conv3d(feats, coords, w, shape) + bias)
+    st = ops.SparseTensor(feats.cuda(), torch.from_numpy(coords).cuda(), None, shape, B)
+    nbr = ops.sp_subm_neighbors(st, (3, 3, 3))
+    wp = w.reshape(cout, 27, cin).permute(1, 2, 0).contiguous().cuda()
+    pk = ops.pack_spconv_tc(wp)
+    fs = ops.rows_to_split(st.feats, None)
+    assert torch.allclose(fs[:, :cin].float() + fs[:, cin:].float(), st.feats, rtol=0, atol=1e-4)
+    out32 = ops.sp_gather_gemm_tc(fs, nbr, None, pk, bias.cuda(), True, cin, cout, want_f32=True)
+    outs = ops.sp_gather_gemm_tc(fs, nbr, None, pk, bias.cuda(), True, cin, cout, want_f32=False)
+    scale = max(ref.abs().max().item(), 1.0)
+    assert (out32.cpu() - ref).abs().max().item() < 1e-4 * scale
+    merged = outs[:, :cout].float() + outs[:, cout:].float()
+    assert (merged.cpu() - ref).abs().max().item() < 1e-4 * scale
+    # a live-row count on the device smaller than the capacity: rows beyond it are not written
+    m_dev = torch.tensor([n // 2], dtype=torch.int32, device="cuda")
+    part = ops.sp_gather_gemm_tc(fs, nbr, m_dev, pk, bias.cuda(), True, cin, cout, want_f32=True)
+    assert torch.equal(part[: n // 2], out32[: n // 2])
+
+
+def test_strided_conv_tensor_core_vs_oracle():
+    from heal_b200 import ops
+    ksize, stride, pad, shape = (3, 3, 3), (2, 2, 2), (1, 1, 1), [41, 64, 64]
+    rng = np.random.default_rng(4242)
+    B, cin, cout = 3, 32, 64
+    feats, coords = _random_sparse(rng, B, shape, 6000, cin)
+    w = torch.from_numpy((rng.standard_normal((cout, *ksize, cin)) / np.sqrt(27 * cin)).astype(np.float32))
+    ref, rc, oshape = sc.sparse_conv3d(feats, coords, w, shape, stride, pad)
+    st = ops.SparseTensor(feats.cuda(), torch.from_numpy(coords).cuda(), None, shape, B)
+    out_st, nbr = ops.sp_strided(st, ksize, stride, pad)
+    m = int(out_st.rows_dev.item())
+    assert m == len(rc)
+    pk = ops.pack_spconv_tc(w.reshape(cout, 27, cin).permute(1, 2, 0).contiguous().cuda())
+    out = ops.sp_gather_gemm_tc(ops.rows_to_split(st.feats, None), nbr, out_st.rows_dev, pk, None, False, cin, cout, want_f32=True)[:m].cpu()
+    order = np.argsort(_lin(out_st.coords[:m].cpu().numpy(), oshape))
+    assert (out[torch.from_numpy(order)] - ref).abs().max().item() < 1e-4 * max(ref.abs().max().item(), 1.0)
+
+
+def test_strided_overflow_is_reported():
+    from heal_b200 import ops
+    rng = np.random.default_rng(1)
+    shape, B = [41, 64, 64], 1
+    feats, coords = _random_sparse(rng, B, shape, 4000, 16)
+    st = ops.SparseTensor(feats.cuda(), torch.from_numpy(coords).cuda(), None, shape, B)
+    out_st, _ = ops.sp_strided(st, (3, 3, 3), (2, 2, 2), (1, 1, 1), out_capacity=100)
+    with pytest.raises(RuntimeError):
+        ops.sp_check_overflow([out_st])
 
 
 def _second_args(rng_):
