@@ -356,7 +356,7 @@ def aggregate_profile(recs, frames, peaks):
     hbm = peaks.get("hbm_gbs", 6577.0)
     tf = peaks.get("bf16_tflops_sustained", 1400.0)
     agg = {}
-    for name, flops, a, b, nbytes in recs:
+    for name, flops, a, b, nbytes, *_ in recs:
         fl = float(flops() if callable(flops) else flops)
         by = float(nbytes() if callable(nbytes) else nbytes)
         d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
@@ -863,6 +863,18 @@ def cuda_eager_leg(wl_name, n_agents, scenes, dev, ref_cpu_out):
         rec["bf16_autocast_note"] = repr(e)[:120]
     if ref_cpu_out is not None:
         rec["fp32_vs_cpu_reference_max_abs"] = {k: float((out32[k].float().cpu() - ref_cpu_out[k]).abs().max()) for k in HEADS if k in out32}
+
+        def rel(o):
+            return max(float((o[k].float().cpu() - ref_cpu_out[k]).abs().max()) / max(float(ref_cpu_out[k].abs().max()), 1.0)
+                       for k in HEADS if k in o)
+        # how far stock PyTorch's own reduced-precision modes are from the fp32 CPU reference on this frame (context for `parity`)
+        try:
+            _, otf = ref_runner.time_cuda_eager(m, data, 1, 1, allow_tf32=True)
+            rec["tf32_max_rel_err_vs_cpu_fp32"] = rel(otf)
+            _, obf = ref_runner.time_cuda_eager(m, data, 1, 1, allow_tf32=True, autocast_bf16=True)
+            rec["bf16_autocast_max_rel_err_vs_cpu_fp32"] = rel(obf)
+        except Exception as e:
+            rec["reduced_precision_err_note"] = repr(e)[:120]
     del m
     torch.cuda.empty_cache()
     return rec

@@ -58,6 +58,13 @@ struct HealArena {
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stg_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// epilogue activation selector shared by the conv kernels: 0 none, 1 ReLU, 2 GELU (exact, erf form: torch.nn.GELU() default)
+__device__ __forceinline__ float heal_act_fn(float v, int mode) {
+    if (mode == 1) return fmaxf(v, 0.f);
+    if (mode == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

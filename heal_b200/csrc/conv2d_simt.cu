@@ -121,7 +121,7 @@ k_conv2d_dense(ConvP p) {
         }
         if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 4; ++j) v[j] = heal_act_fn(v[j], p.relu);
         }
         if (co + 3 < p.Cout && ((p.out.cs | p.out.co) & 3) == 0) {
             act_store4(p.out, pix, co, make_float4(v[0], v[1], v[2], v[3]));
@@ -204,7 +204,7 @@ k_conv2d_grouped(ConvP p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float t = acc[i][q * 4 + j] + bv[q * 4 + j];
-                    v[j] = p.relu ? fmaxf(t, 0.f) : t;
+                    v[j] = heal_act_fn(t, p.relu);
                 }
                 act_store4(p.out, pix, g * CG + co0 + q * 4, make_float4(v[0], v[1], v[2], v[3]));
             }

@@ -52,7 +52,7 @@ struct TcP {
     int wplanes;                  // WEIGHT planes: 2 = split weights (hi + lo).  planes 1 + wplanes 2 = the 'bf16' engine mode:
                                   // bf16 activations x un-rounded (16-mantissa-bit) weights, a_hi x [b_hi | b_lo]
     int coutp;                    // padded Cout rows per tap in the weight matrix (multiple of BLOCK_N)
-    int relu;
+    int relu;                     // epilogue activation: 0 none, 1 ReLU, 2 GELU (erf)
     int up;                       // transposed conv (k == stride == up): n-tile -> (i,j) sub-position
     int pdl;                      // launched with programmatic stream serialization
     int bo_mode;                  // experiment: base-offset convention of the halo descriptors
@@ -420,9 +420,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
                         }
-                        if (p.relu) {
+                        if (p.relu == 1) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.relu == 2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = heal_act_fn(v[j], 2);
                         }
                         float lo[8];
 #pragma unroll
@@ -493,9 +496,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
                             for (int j = 0; j < 8 && c + j < p.Cout; ++j) v[j] += __ldg(rp + j);
                         }
-                        if (p.relu) {
+                        if (p.relu == 1) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.relu == 2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = heal_act_fn(v[j], 2);
                         }
                         if (p.out_split && !((p.dbg & 1) && v[0] != 1.2345e30f)) {
                             __nv_bfloat16* op = p.out_split + pix * p.out_cs + p.out_co + c;

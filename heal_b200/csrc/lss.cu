@@ -7,6 +7,7 @@
 // The (n*cams, C, D, fH, fW) outer-product tensor of the reference (277 MB per agent at 704x256) is never
 // materialised: each block stages one image row of depth logits and features in shared memory, computes the
 // softmax in place and accumulates prob*feat straight into the channels-last BEV map.
+#include <cub/cub.cuh>
 #include "common.cuh"
 #include "../../include/heal_b200.h"
 
@@ -104,7 +105,143 @@ k_lss_pool(PoolP p) {
     }
 }
 
+// ---- deterministic BEV pooling: cell-sorted interval reduction (no atomics) -----------------------------------------------------
+// keys = agent * cells + cell (invalid points get the one-past-the-end key), values = frustum point id; a STABLE radix sort puts
+// every BEV cell's points next to each other in ascending point order; one warp per cell then sums prob * feature over its
+// interval in that fixed order and writes the cell's C channels once (empty cells are written as zeros: no memset pass).
+struct SortedP {
+    const float* logits; long long l_img, l_d, l_pix;     // depth logits, element strides (NCHW trunk: HW*D, HW, 1; NHWC heads: HW*S, 1, S)
+    const float* feat;   long long f_img, f_c, f_pix;     // image features
+    const int* cell;                                        // (BN, D, fH, fW)
+    int BN, cams, D, C, HW, cells_per_agent, agents;
+    float* prob;                                            // (BN, D, HW) workspace
+    ActV out;                                               // (agents, cells_per_agent, C) channels-last, any storage format
+};
+
+__global__ void k_lss_keys(const int* __restrict__ cell, long long n, int DHW, int cams, int cells_per_agent, unsigned invalid,
+                           unsigned* __restrict__ keys, int* __restrict__ vals) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell[i];
+    const int agent = (int)(i / DHW) / cams;
+    keys[i] = (c < 0) ? invalid : (unsigned)agent * (unsigned)cells_per_agent + (unsigned)c;
+    vals[i] = (int)i;
+}
+
+// softmax over D for every (image, pixel): one thread per pixel (D = 48: the logits of a pixel are contiguous for NHWC heads)
+__global__ void k_lss_prob(SortedP p) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.BN * p.HW) return;
+    const int bn = (int)(t / p.HW), pix = (int)(t % p.HW);
+    const float* lg = p.logits + (long long)bn * p.l_img + (long long)pix * p.l_pix;
+    float mx = -INFINITY;
+    for (int d = 0; d < p.D; ++d) mx = fmaxf(mx, __ldg(lg + d * p.l_d));
+    float s = 0.f;
+    for (int d = 0; d < p.D; ++d) s += expf(__ldg(lg + d * p.l_d) - mx);
+    float* pr = p.prob + ((size_t)bn * p.D) * p.HW + pix;
+    for (int d = 0; d < p.D; ++d) pr[(size_t)d * p.HW] = expf(__ldg(lg + d * p.l_d) - mx) / s;
+}
+
+__global__ void k_lss_starts(const unsigned* __restrict__ keys, long long n, unsigned total_cells, int* __restrict__ start) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys[i];
+    if (k < total_cells && (i == 0 || keys[i - 1] != k)) start[k] = (int)i;
+}
+
+// one warp per BEV cell; lane covers channels lane, lane+32, ... (C <= 256)
+__global__ void __launch_bounds__(256)
+k_lss_pool_cells(SortedP p, const unsigned* __restrict__ keys, const int* __restrict__ vals, const int* __restrict__ start, long long n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cellg = (long long)blockIdx.x * 8 + warp;
+    const long long total = (long long)p.agents * p.cells_per_agent;
+    if (cellg >= total) return;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    const int s = start[cellg];
+    if (s >= 0) {
+        const int DHW = p.D * p.HW;
+        for (long long j = s; j < n && keys[j] == (unsigned)cellg; ++j) {
+            const int i = vals[j];
+            const int bn = i / DHW, pix = (i - bn * DHW) % p.HW;
+            const float pr = p.prob[i];
+            const float* f = p.feat + (long long)bn * p.f_img + (long long)pix * p.f_pix;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = q * 32 + lane;
+                if (c < p.C) acc[q] = fmaf(pr, __ldg(f + (long long)c * p.f_c), acc[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int c = q * 32 + lane;
+        if (c < p.C) act_store1(p.out, (size_t)cellg, c, acc[q]);
+    }
+}
+
+struct SortedWs { size_t keys_in, keys_out, vals_in, vals_out, prob, start, cub, total, cub_bytes; };
+
+SortedWs sorted_layout(long long npts, long long total_cells, int end_bit) {
+    SortedWs L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = heal_align_up(o + bytes, 256); return r; };
+    L.keys_in = take(npts * 4); L.keys_out = take(npts * 4); L.vals_in = take(npts * 4); L.vals_out = take(npts * 4);
+    L.prob = take(npts * 4); L.start = take(total_cells * 4);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr,
+                                    (int)npts, 0, end_bit);
+    L.cub_bytes = tb;
+    L.cub = take(tb);
+    L.total = o + 256;
+    return L;
+}
+
+int key_bits(long long total_cells) { int b = 1; while ((1LL << b) <= total_cells) ++b; return b; }
+
 }  // namespace
+
+extern "C" size_t heal_lss_pool_sorted_workspace(int num_images, int D, int fH, int fW, int agents, int cells_per_agent) {
+    const long long npts = (long long)num_images * D * fH * fW, cells = (long long)agents * cells_per_agent;
+    if (npts <= 0 || cells <= 0 || npts >= (1LL << 31)) return 0;
+    return sorted_layout(npts, cells, key_bits(cells)).total;
+}
+
+extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, long long l_d, long long l_pix,
+                                    const float* feat, long long f_img, long long f_c, long long f_pix,
+                                    const int* cell, int num_images, int cams_per_agent, int D, int C, int fH, int fW,
+                                    int cells_per_agent, const heal_act_t* bev_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!depth_logits || !feat || !cell || !bev_out || !bev_out->data || !workspace) return HEAL_ERR_ARG;
+    if (num_images <= 0) return HEAL_OK;
+    if (cams_per_agent < 1 || (num_images % cams_per_agent) || C < 1 || C > 256) return HEAL_ERR_ARG;
+    const int agents = num_images / cams_per_agent;
+    const long long npts = (long long)num_images * D * fH * fW, cells = (long long)agents * cells_per_agent;
+    if (npts >= (1LL << 31) || cells >= (1LL << 31)) return HEAL_ERR_UNSUPPORTED;
+    const int bits = key_bits(cells);
+    SortedWs L = sorted_layout(npts, cells, bits);
+    if (workspace_bytes < L.total) return HEAL_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream_;
+    SortedP p;
+    p.logits = depth_logits; p.l_img = l_img; p.l_d = l_d; p.l_pix = l_pix;
+    p.feat = feat; p.f_img = f_img; p.f_c = f_c; p.f_pix = f_pix;
+    p.cell = cell; p.BN = num_images; p.cams = cams_per_agent; p.D = D; p.C = C; p.HW = fH * fW;
+    p.cells_per_agent = cells_per_agent; p.agents = agents; p.prob = (float*)(ws + L.prob);
+    p.out.p = bev_out->data; p.out.fmt = bev_out->fmt; p.out.cs = bev_out->cstride; p.out.co = bev_out->coffset; p.out.plane = bev_out->plane_stride;
+    unsigned* k_in = (unsigned*)(ws + L.keys_in); unsigned* k_out = (unsigned*)(ws + L.keys_out);
+    int* v_in = (int*)(ws + L.vals_in); int* v_out = (int*)(ws + L.vals_out);
+    int* start = (int*)(ws + L.start);
+    const unsigned gp = (unsigned)((npts + 255) / 256);
+    k_lss_keys<<<gp, 256, 0, st>>>(cell, npts, D * fH * fW, cams_per_agent, cells_per_agent, (unsigned)cells, k_in, v_in);
+    k_lss_prob<<<(unsigned)(((long long)num_images * p.HW + 127) / 128), 128, 0, st>>>(p);
+    size_t tb = L.cub_bytes;
+    if (cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, k_in, k_out, v_in, v_out, (int)npts, 0, bits, st) != cudaSuccess) return HEAL_ERR_LAUNCH;
+    cudaMemsetAsync(start, 0xFF, (size_t)cells * 4, st);
+    k_lss_starts<<<gp, 256, 0, st>>>(k_out, npts, (unsigned)cells, start);
+    k_lss_pool_cells<<<(unsigned)((cells + 7) / 8), 256, 0, st>>>(p, k_out, v_out, start, npts);
+    return heal_check_launch(6);
+}
 
 extern "C" int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,
                                    const float* post_rots_inv, const float* post_trans, const float* combine, const float* trans,

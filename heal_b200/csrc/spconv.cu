@@ -75,7 +75,7 @@ __global__ void k_sp_subm_nbr(const int4* __restrict__ coords, const int* __rest
 
 // strided conv, pass 1: each (input i, offset k) proposes an output site; the smallest proposer id wins the site
 __global__ void k_sp_propose(const int4* __restrict__ coords, const int* __restrict__ m_dev, int M, SpGeom go, KShape ks,
-                             uint32_t* __restrict__ okeys, int* __restrict__ ofirst, int* __restrict__ cand_slot) {
+                             uint32_t* __restrict__ okeys, int* __restrict__ ofirst, int* __restrict__ cand_slot, int* __restrict__ overflow) {
     const int K = ks.kz * ks.ky * ks.kx;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
@@ -90,13 +90,20 @@ __global__ void k_sp_propose(const int4* __restrict__ coords, const int* __restr
         if (oz < go.Z && oy < go.Y && ox < go.X) {
             uint32_t key = sp_key(c.x, oz, oy, ox, go);
             uint32_t s = sp_hash(key, go);
-            while (true) {
+            // The table holds 2 x out_capacity slots.  With more distinct output sites than slots (an undersized capacity) an
+            // unbounded probe would spin forever: give up after one sweep, drop the candidate and raise the overflow flag.
+            bool found = false;
+            for (uint32_t probe = 0; probe <= go.tmask; ++probe) {
                 uint32_t prev = atomicCAS(&okeys[s], SP_EMPTY, key);
-                if (prev == SP_EMPTY || prev == key) break;
+                if (prev == SP_EMPTY || prev == key) { found = true; break; }
                 s = (s + 1) & go.tmask;
             }
-            atomicMin(&ofirst[s], (int)t);
-            slot = (int)s;
+            if (found) {
+                atomicMin(&ofirst[s], (int)t);
+                slot = (int)s;
+            } else {
+                atomicExch(overflow, 1);
+            }
         }
     }
     cand_slot[t] = slot;
@@ -179,6 +186,11 @@ __global__ void k_sp_assign(const int4* __restrict__ coords, const int* __restri
             ++rank;
         }
     }
+}
+
+// a full hash table dropped candidates: report more rows than the capacity so that callers see the overflow
+__global__ void k_sp_flag_overflow(const int* __restrict__ overflow, int cap, int* __restrict__ out_rows) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && overflow[0] && out_rows[0] <= cap) out_rows[0] = cap + 1;
 }
 
 // pass 4: nbr[out_row][k] = i
@@ -307,7 +319,7 @@ extern "C" size_t heal_spconv_strided_workspace(int in_capacity, int out_capacit
     size_t M = (size_t)(in_capacity > 0 ? in_capacity : 1);
     size_t ts = (size_t)1 << table_log2(out_capacity > 0 ? out_capacity : 1);
     return heal_align_up(M * kvol * 4, 256) + heal_align_up(M * 4, 256) * 2 + heal_align_up((M / SP_SCAN + 4) * 4, 256) +
-           heal_align_up(ts * 4, 256) + 4096;
+           heal_align_up(ts * 4, 256) + 256 + 4096;
 }
 
 extern "C" int heal_spconv_strided_rulebook(const int* in_coords, const int* in_rows_dev, int in_capacity,
@@ -337,20 +349,23 @@ extern "C" int heal_spconv_strided_rulebook(const int* in_coords, const int* in_
     int nb = (in_capacity + SP_SCAN - 1) / SP_SCAN;
     int* block_off = ar.take<int>(nb + 2);
     int* ofirst = ar.take<int>(ts);                        // per site: smallest proposer id (input row * K + offset)
+    int* overflow = ar.take<int>(1);
     if (!ar.ok()) return HEAL_ERR_WORKSPACE;
+    cudaMemsetAsync(overflow, 0, 4, st);
     cudaMemsetAsync(out_table_keys, 0xFF, ts * 4, st);
     cudaMemsetAsync(ofirst, 0x7F, ts * 4, st);
     cudaMemsetAsync(nbr_out, 0xFF, (size_t)out_capacity * K * 4, st);
     long long total = (long long)in_capacity * K;
     unsigned gt = (unsigned)((total + 255) / 256), gm = (unsigned)((in_capacity + 255) / 256);
-    k_sp_propose<<<gt, 256, 0, st>>>((const int4*)in_coords, in_rows_dev, in_capacity, go, ks, out_table_keys, ofirst, cand_slot);
+    k_sp_propose<<<gt, 256, 0, st>>>((const int4*)in_coords, in_rows_dev, in_capacity, go, ks, out_table_keys, ofirst, cand_slot, overflow);
     k_sp_count_first<<<gm, 256, 0, st>>>(in_rows_dev, in_capacity, K, ofirst, cand_slot, cnt);
     k_sp_scan_local<<<nb, SP_SCAN, 0, st>>>(cnt, in_capacity, local_excl, block_off);
     k_sp_scan_blocks<<<1, SP_SCAN, 0, st>>>(block_off, nb, out_rows_dev);
     k_sp_assign<<<gm, 256, 0, st>>>((const int4*)in_coords, in_rows_dev, in_capacity, go, ks, out_table_keys, ofirst, cand_slot,
                                     local_excl, block_off, out_capacity, out_table_vals, (int4*)out_coords);
     k_sp_link<<<gt, 256, 0, st>>>(in_rows_dev, in_capacity, K, cand_slot, out_table_vals, nbr_out);
-    return heal_check_launch(6);
+    k_sp_flag_overflow<<<1, 32, 0, st>>>(overflow, out_capacity, out_rows_dev);
+    return heal_check_launch(7);
 }
 
 extern "C" int heal_spconv_gather_gemm(const float* in_feats, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,

@@ -1,5 +1,7 @@
 """Per-modality encoders with the reference's `(data_dict, modality_name) -> (n,C,H,W)` signature
 (opencood/models/heter_encoders.py:22-301).  PointPillar runs PillarVFE + scatter as one kernel."""
+import os as _os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -84,9 +86,15 @@ def depth_discretization(depth_min, depth_max, num_bins, mode):
 
 class CamEncode_Resnet101(nn.Module):
     """Image trunk + depth / image heads (opencood/models/sub_modules/lss_submodule.py:140-233), same attribute
-    names -> same state-dict keys.  The trunk (first two ResNet-101 stages) is a 'next' row and
-    runs on PyTorch/cuDNN; the depth softmax (x) feature outer product that follows it is NOT computed here - it
-    is fused into the BEV-pool kernel."""
+    names -> same state-dict keys (the torchvision modules are parameter containers).  `heads_nhwc` runs the whole trunk on
+    the conv engine:
+      conv1 7x7/2 + bn1 + ReLU   as a 3x3 convolution on the 4x4 space-to-depth image (3 -> 64 input channels, 4 output phases
+                                 x 64 channels): a tcgen05 shape instead of a K = 3 stem; exact re-indexing of the same sums
+      maxpool 3x3/2              heal_maxpool3x3s2 reading the phase-major stem output directly
+      layer1, layer2             torchvision Bottlenecks: 1x1 / 3x3 (stride) / 1x1 + residual, each conv+BN(+ReLU) one kernel
+      depth_head | image_head    one fused 1x1 convolution 512 -> D + C, fp32 channels-last output
+    The depth softmax (x) feature outer product that follows is NOT computed here - it is fused into the BEV-pool kernel.
+    `heads` keeps the plain torch path (CPU-capable; the tests' oracle trunk)."""
 
     def __init__(self, D, C, downsample, ddiscr, mode, use_gt_depth=False, depth_supervision=True):
         super().__init__()
@@ -106,6 +114,84 @@ class CamEncode_Resnet101(nn.Module):
         """x (BN, 3|4, H, W) -> (depth_logits (BN,D,fH,fW), feat (BN,C,fH,fW))"""
         f = self.layer2(self.layer1(self.maxpool(self.relu(self.bn1(self.conv1(x[:, :3].clone()))))))
         return self.depth_head(f), self.image_head(f)
+
+    # ---- conv-engine path -------------------------------------------------------------------------------------------
+    def _stem_as_s2d_conv(self):
+        """conv1 (64,3,7,7, stride 2, pad 3) + bn1 folded -> Conv2d(64, 256, 3, pad 1, bias) acting on pixel_unshuffle(x, 4):
+        input channel = c*16 + dy*4 + dx (c < 3; c == 3 is zero padding), output channel = (py*2 + px)*64 + co where the
+        output pixel is (2Y + py, 2X + px).  out(2Y+py, 2X+px) = sum_{r,s} W[r,s] in(4Y + 2py - 3 + r, 4X + 2px - 3 + s):
+        with block offset b in {-1,0,1} and in-block row d, r = 4b + d - 2py + 3."""
+        from ..engine import _sig
+        sig = _sig(self.conv1, self.bn1)
+        hit = getattr(self, "_stem_cache", None)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        w = self.conv1.weight.detach().double().cpu()                       # (64, 3, 7, 7)
+        bn = self.bn1
+        scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+        shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+        w = w * scale[:, None, None, None]
+        wn = torch.zeros((4, 64, 4, 16, 3, 3), dtype=torch.float64)          # (phase, co, c, dy*4+dx, by, bx)
+        for py in range(2):
+            for px in range(2):
+                for by in range(3):
+                    for dy in range(4):
+                        r = 4 * (by - 1) + dy - 2 * py + 3
+                        if not (0 <= r < 7):
+                            continue
+                        for bx in range(3):
+                            for dx in range(4):
+                                q = 4 * (bx - 1) + dx - 2 * px + 3
+                                if 0 <= q < 7:
+                                    wn[py * 2 + px, :, :3, dy * 4 + dx, by, bx] = w[:, :, r, q]
+        conv = nn.Conv2d(64, 256, 3, padding=1, bias=True)
+        with torch.no_grad():
+            conv.weight.copy_(wn.reshape(256, 64, 3, 3).float())
+            conv.bias.copy_(shift.repeat(4).float())
+        conv = conv.to(self.conv1.weight.device)
+        self.__dict__["_stem_cache"] = (sig, conv)                            # not a registered submodule: no state-dict keys
+        return conv
+
+    def _fused_heads(self):
+        from ..engine import _sig
+        sig = _sig(self.depth_head, self.image_head)
+        hit = getattr(self, "_heads_cache", None)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        conv = nn.Conv2d(512, self.D + self.C, 1).to(self.depth_head.weight.device)
+        with torch.no_grad():
+            conv.weight.copy_(torch.cat([self.depth_head.weight, self.image_head.weight], 0))
+            conv.bias.copy_(torch.cat([self.depth_head.bias, self.image_head.bias], 0))
+        self.__dict__["_heads_cache"] = (sig, conv)
+        return conv
+
+    @staticmethod
+    def _bottleneck_nhwc(blk, x):
+        """torchvision.models.resnet.Bottleneck.forward on the conv engine (stride on the 3x3, ResNet v1.5)."""
+        from ..engine import conv_bn_act
+        idt = x
+        if blk.downsample is not None:
+            idt = conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False)
+        y = conv_bn_act(x, blk.conv1, blk.bn1, relu=True)
+        y = conv_bn_act(y, blk.conv2, blk.bn2, relu=True)
+        return conv_bn_act(y, blk.conv3, blk.bn3, relu=True, residual=idt)
+
+    def heads_nhwc(self, x):
+        """x (BN, 3|4, H, W) fp32 CUDA -> Act f32 (BN, H/8, W/8, D + C): [depth logits | image features] per pixel."""
+        from ..engine import conv_bn_act
+        BN, Cx, H, W = x.shape
+        if (H % 8) or (W % 8):
+            raise NotImplementedError("image sides must be multiples of 8 (the LSS yamls use img_downsample 8)")
+        x4 = torch.zeros((BN, 4, H, W), dtype=torch.float32, device=x.device)
+        x4[:, :3] = x[:, :3]
+        a = ops.to_act(torch.nn.functional.pixel_unshuffle(x4, 4))          # (BN, H/4, W/4, 64): layout plumbing of the raw image
+        y = conv_bn_act(a, self._stem_as_s2d_conv(), None, relu=True)         # phase-major (BN, H/4, W/4, 4*64) = logical (BN, H/2, W/2, 64)
+        y = ops.maxpool3x3s2(y, depth_to_space_in=True)                       # (BN, H/4, W/4, 64)
+        for blk in self.layer1:
+            y = self._bottleneck_nhwc(blk, y)
+        for blk in self.layer2:
+            y = self._bottleneck_nhwc(blk, y)
+        return conv_bn_act(y, self._fused_heads(), None, relu=False, out_fmt="f32")
 
 
 class LiftSplatShoot(nn.Module):
@@ -153,15 +239,35 @@ class LiftSplatShoot(nn.Module):
                                   lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
         return ops.lss_pool(depth_logits, feat, cell, N, int(self.nx[0]), int(self.nx[1]))
 
+    def cell_index(self, rots, trans, intrins, post_rots, post_trans):
+        B, N = trans.shape[:2]
+        post_inv = torch.inverse(post_rots).reshape(B * N, 3, 3)          # 3x3 algebra exactly as the reference (:135,:142)
+        combine = rots.matmul(torch.inverse(intrins)).reshape(B * N, 3, 3)
+        lower = (self.bx - self.dx / 2.).tolist()
+        return ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
+                                  lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
+
     def forward_act(self, data_dict, modality_name, fmt=None):
+        """image trunk + heads on the conv engine -> frustum cell index -> deterministic sorted BEV pooling
+        (heal_lss_pool_sorted reads logits and features straight from the fused heads' channels-last output)."""
+        from ..engine import act_fmt
         require_eval(self)
         d = data_dict[f'inputs_{modality_name}']
         x = d['imgs']
         B, N, C, imH, imW = x.shape
-        depth_logits, feat = self.camencode.heads(x.view(B * N, C, imH, imW))
+        if _os.environ.get("HEAL_CAM_TRUNK_TORCH", "0") == "1":           # A/B hook: torch / cuDNN trunk + atomic pooling (round 1)
+            depth_logits, feat = self.camencode.heads(x.view(B * N, C, imH, imW))
+            if self.depth_supervision:
+                self.depth_items = (depth_logits, None)
+            return self.bev_from_heads(depth_logits, feat, d['rots'], d['trans'], d['intrins'], d['post_rots'], d['post_trans'])
+        y = self.camencode.heads_nhwc(x.view(B * N, C, imH, imW))         # Act f32 (BN, fH, fW, D + camC)
+        D, camC, fH, fW = self.D, self.camC, y.H, y.W
+        S, HW = D + camC, y.H * y.W
         if self.depth_supervision:
-            self.depth_items = (depth_logits, None)
-        return self.bev_from_heads(depth_logits, feat, d['rots'], d['trans'], d['intrins'], d['post_rots'], d['post_trans'])
+            self.depth_items = (y.t[..., :D].permute(0, 3, 1, 2), None)
+        cell = self.cell_index(d['rots'], d['trans'], d['intrins'], d['post_rots'], d['post_trans'])
+        return ops.lss_pool_sorted(y.t, (HW * S, 1, S), y.t[..., D:], (HW * S, 1, S), cell, N, D, camC, fH, fW,
+                                   int(self.nx[0]), int(self.nx[1]), out_fmt=fmt or act_fmt())
 
     def forward(self, data_dict, modality_name):
         return ops.act_to_nchw(self.forward_act(data_dict, modality_name))

@@ -126,7 +126,7 @@ class HeterPyramidCollab(nn.Module):
             f = enc.forward_act(data_dict, m) if hasattr(enc, "forward_act") else ops.to_act(enc(data_dict, m))
             bb = getattr(self, f"backbone_{m}")
             f = bb.decode_nhwc(bb.multiscale_nhwc(f))                             # Act
-            # aligner_m is the identity for every in-scope modality (AlignNet raises otherwise)
+            f = getattr(self, f"aligner_{m}").forward_nhwc(f)                     # identity, or the ConvNeXt aligner (HEAL stage 2)
             if self.sensor_type_dict[m] == "camera":
                 f = self._center_crop_nhwc(f, int(f.H * getattr(self, f"crop_ratio_H_{m}")),
                                            int(f.W * getattr(self, f"crop_ratio_W_{m}")))

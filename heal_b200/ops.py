@@ -72,13 +72,14 @@ class _Prof:
         if PROFILE is not None:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
+            self.l0 = lib.heal_launch_count()
             self.a.record()
         return self
 
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.b.record()
-            PROFILE.append((self.name, self.work, self.a, self.b, self.nbytes))
+            PROFILE.append((self.name, self.work, self.a, self.b, self.nbytes, int(lib.heal_launch_count() - self.l0)))
         return False
 
 
@@ -511,7 +512,7 @@ def conv2d_simt(x: Act, pc: PackedConv, residual: Optional[Act] = None, out: Opt
                 rc = lib.heal_conv2d_simt(ctypes.byref(xv), N, H, W, cin, _p(wptr), pc.w_cstride, _p(pc.bias),
                                           pc.kh, pc.kw, pc.stride, pc.pad, pc.groups,
                                           ctypes.byref(rv) if rv is not None else None, ctypes.byref(ov),
-                                          Ho, Wo, pc.cout, up, i, j, 1 if pc.relu else 0, st)
+                                          Ho, Wo, pc.cout, up, i, j, int(pc.relu), st)
                 check(rc, "heal_conv2d_simt")
     return out
 
@@ -553,9 +554,43 @@ def conv2d_tc(x: Act, pc: PackedConvTC, residual: Optional[Act] = None, out: Opt
                                 out.cstride if out is not None else 0, out_coffset,
                                 _p(out_f32.t) if out_f32 is not None else _vp(0),
                                 out_f32.cstride if out_f32 is not None else 0, out32_coffset,
-                                Ho, Wo, pc.cout, up, 1 if pc.relu else 0, _stream())
+                                Ho, Wo, pc.cout, up, int(pc.relu), _stream())
     check(rc, "heal_conv2d_tc")
     return out, out_f32
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvNeXt aligner front half, ResNet-stem max pooling
+# ------------------------------------------------------------------------------------------------
+def dwconv_layernorm(x: Act, dw_weight: torch.Tensor, dw_bias, ksize: int, ln_weight, ln_bias, eps: float,
+                     out_fmt: Optional[str] = None) -> Act:
+    """depthwise ksize x ksize conv (+bias) + LayerNorm over channels.  dw_weight (ksize*ksize, C) fp32 tap-major."""
+    _need_cuda(dw_weight, ln_weight, ln_bias)
+    N, H, W, C = x.N, x.H, x.W, x.C
+    assert dw_weight.shape == (ksize * ksize, C) and dw_weight.is_contiguous()
+    out = act_empty(N, H, W, C, out_fmt or x.fmt, x.device)
+    xv, ov = x.view(), out.view()
+    lw, lb = ln_weight.float().contiguous(), ln_bias.float().contiguous()
+    with _Prof("dwconv_layernorm", 2.0 * N * H * W * C * ksize * ksize, N * H * W * float(C) * (BPE[x.fmt] + BPE[out.fmt])):
+        rc = lib.heal_dwconv_layernorm(ctypes.byref(xv), N, H, W, C, _p(dw_weight), _p(dw_bias), int(ksize), _p(lw), _p(lb),
+                                       float(eps), ctypes.byref(ov), _stream())
+    check(rc, "heal_dwconv_layernorm")
+    return out
+
+
+def maxpool3x3s2(x: Act, out_fmt: Optional[str] = None, depth_to_space_in: bool = False) -> Act:
+    """3x3 / stride 2 / pad 1 max pooling (torchvision ResNet stem).  depth_to_space_in: x is (N,H/2,W/2,4C) phase-major
+    (channel block (y&1)*2+(x&1)) and stands for the logical (N,H,W,C) map."""
+    N, H, W, C = x.N, x.H, x.W, x.C
+    if depth_to_space_in:
+        H, W, C = 2 * H, 2 * W, C // 4
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = act_empty(N, Ho, Wo, C, out_fmt or x.fmt, x.device)
+    xv, ov = x.view(), out.view()
+    with _Prof("maxpool3x3s2", 0, N * float(C) * (H * W * BPE[x.fmt] + Ho * Wo * BPE[out.fmt])):
+        rc = lib.heal_maxpool3x3s2(ctypes.byref(xv), N, H, W, C, 1 if depth_to_space_in else 0, ctypes.byref(ov), _stream())
+    check(rc, "heal_maxpool3x3s2")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -640,6 +675,28 @@ def lss_pool(depth_logits, feat, cell, cams_per_agent: int, nx, ny) -> Act:
     return Act(out, "f32")
 
 
+def lss_pool_sorted(logits: torch.Tensor, l_strides, feat: torch.Tensor, f_strides, cell: torch.Tensor, cams_per_agent: int,
+                    D: int, C: int, fH: int, fW: int, nx: int, ny: int, out_fmt: str = "f32") -> Act:
+    """Deterministic LSS pooling (heal_lss_pool_sorted).  `logits` / `feat` are fp32 tensors whose data_ptr is the first logit /
+    feature element, described by ELEMENT strides (image, depth-bin | channel, pixel); cell (BN,D,fH,fW) i32.
+    Returns Act (agents, ny, nx, C) in `out_fmt` (written completely: no memset)."""
+    _need_cuda(logits, feat, cell)
+    assert logits.dtype == torch.float32 and feat.dtype == torch.float32 and cell.dtype == torch.int32 and cell.is_contiguous()
+    BN = cell.shape[0]
+    agents = BN // cams_per_agent
+    out = act_empty(agents, ny, nx, C, out_fmt, feat.device)
+    wsb = lib.heal_lss_pool_sorted_workspace(BN, D, fH, fW, agents, nx * ny)
+    ws = _workspace(feat.device, wsb)
+    ov = out.view()
+    npts = BN * D * fH * fW
+    with _Prof("lss_pool_sorted", 2.0 * npts * C, BN * fH * fW * 4.0 * (2 * D + C) + agents * float(ny) * nx * C * BPE[out_fmt]):
+        rc = lib.heal_lss_pool_sorted(_p(logits), int(l_strides[0]), int(l_strides[1]), int(l_strides[2]),
+                                      _p(feat), int(f_strides[0]), int(f_strides[1]), int(f_strides[2]),
+                                      _p(cell), BN, cams_per_agent, D, C, fH, fW, nx * ny, ctypes.byref(ov), _p(ws), ws.numel(), _stream())
+    check(rc, "heal_lss_pool_sorted")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # sparse 3-D convolution (SECOND)
 # ------------------------------------------------------------------------------------------------
@@ -690,7 +747,7 @@ def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
     return nbr
 
 
-SP_GROWTH = 1.5     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
+SP_GROWTH = 2.0     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
 
 
 def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int] = None):
@@ -961,7 +1018,7 @@ def _guard(fn):
     return wrapped
 
 
-for _name in ("convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
-              "lss_cell_index", "lss_pool", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
+for _name in ("dwconv_layernorm", "maxpool3x3s2", "convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
+              "lss_cell_index", "lss_pool", "lss_pool_sorted", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
               "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
     globals()[_name] = _guard(globals()[_name])

@@ -186,6 +186,18 @@ int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,
 int heal_lss_pool(const float* depth_logits, const float* feat, const int* cell, int num_images, int cams_per_agent,
                   int D, int C, int fH, int fW, int cells_per_agent, float* bev_out, void* stream);
 
+/* Deterministic variant of heal_lss_pool (the default path): cell-sorted interval reduction, no atomics.  Points are radix-sorted
+ * (stable, CUB) by agent*cells + cell; one warp per BEV cell sums prob * feature over the cell's interval in ascending point
+ * order and writes the cell's channels once -- every run gives the same bits (the reference's QuickCumsum,
+ * opencood/utils/camera_utils.py:220-246, is likewise a sum over a sorted interval).  No memset of the BEV map.
+ *   depth_logits / feat with ELEMENT strides (image, depth-bin | channel, pixel): NCHW torch tensors (HW*D, HW, 1) or the
+ *   channels-last output of the fused 1x1 heads (HW*S, 1, S).  bev_out: (agents, cells_per_agent, C) channels-last view, any format. */
+size_t heal_lss_pool_sorted_workspace(int num_images, int D, int fH, int fW, int agents, int cells_per_agent);
+int heal_lss_pool_sorted(const float* depth_logits, long long l_img, long long l_d, long long l_pix,
+                         const float* feat, long long f_img, long long f_c, long long f_pix,
+                         const int* cell, int num_images, int cams_per_agent, int D, int C, int fH, int fW,
+                         int cells_per_agent, const heal_act_t* bev_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- sparse 3-D convolution (SECOND VoxelBackBone8x) + HeightCompression ------------------------
  * Replaces the spconv calls of opencood/models/sub_modules/sparse_backbone_3d.py:48-91,:114-130 and
  * height_compression.py:21-23.  A sparse tensor = feats (rows,C) f32 + coords (rows,4) i32 [b,z,y,x] + a device
@@ -248,6 +260,20 @@ int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal
 
 /* ---- format conversion between fp32 and (split-)bf16 channels-last buffers ------------------- */
 int heal_act_convert(const heal_act_t* src, const heal_act_t* dst, size_t num_pixels, int channels, void* stream);
+
+/* ---- ConvNeXt aligner -------------------------------------------------------------
+ * depthwise k x k conv (+bias) + LayerNorm over channels, one kernel: the front half of ConvNeXtBlock.forward
+ * (opencood/models/sub_modules/feature_alignnet_modules.py:331-336, LayerNorm :12-25 channels_last, biased variance).
+ *   dw_weight [k*k][C] fp32 (tap-major), dw_bias [C] or NULL, ln_weight / ln_bias [C]; C in {64,128,192,256}
+ * The two Linear layers that follow are 1x1 convolutions on heal_conv2d_tc (`relu` = 2 selects the exact erf GELU in the
+ * epilogue; layer scale `gamma` folded into the second one; the block's residual add is the conv's residual input). */
+int heal_dwconv_layernorm(const heal_act_t* in, int N, int H, int W, int C, const float* dw_weight, const float* dw_bias,
+                          int ksize, const float* ln_weight, const float* ln_bias, float eps, const heal_act_t* out, void* stream);
+
+/* 3x3 / stride 2 / pad 1 max pooling, channels-last (torchvision ResNet stem of CamEncode_Resnet101,
+ * opencood/models/sub_modules/lss_submodule.py:196-199).  depth_to_space_in != 0: the logical (N,H,W,C) input is stored as
+ * (N,H/2,W/2,4C) with channel block (y&1)*2+(x&1) -- the phase-major output of the space-to-depth form of the 7x7/2 stem conv. */
+int heal_maxpool3x3s2(const heal_act_t* in, int N, int H, int W, int C, int depth_to_space_in, const heal_act_t* out, void* stream);
 
 #ifdef __cplusplus
 }

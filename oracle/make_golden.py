@@ -179,9 +179,25 @@ def main():
                 "out": {k: bout[k] for k in ("cls_preds", "reg_preds", "dir_preds")}},
                os.path.join(OUT, "heter_model_baseline_att_small.pt"))
     print("heter_model_baseline_att_small:", {k: tuple(v.shape) for k, v in bout.items() if torch.is_tensor(v)})
+    make_convnext_golden()
     make_postprocess_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+def make_convnext_golden():
+    """UNMODIFIED reference AlignNet(core_method='convnext') (feature_alignnet.py:12-39 -> feature_alignnet_modules.ConvNeXt)."""
+    ref_shim.install()
+    from opencood.models.sub_modules.feature_alignnet import AlignNet
+    cfg = {"core_method": "convnext", "spatial_align": False, "args": {"num_of_blocks": 3, "dim": 64}}
+    m = AlignNet(copy.deepcopy(cfg)).eval()
+    shapes = procedural.shapes_of(m)
+    m.load_state_dict(procedural.make_state_dict(shapes), strict=True)
+    x = torch.randn(2, 64, 24, 40, generator=torch.Generator().manual_seed(31))
+    with torch.no_grad():
+        y = m(x)
+    torch.save({"cfg": cfg, "shapes": shapes, "x": x, "y": y}, os.path.join(OUT, "convnext_aligner.pt"))
+    print("convnext_aligner:", tuple(y.shape), float(y.abs().max()), float((y - x).abs().max()))
 
 
 def postprocess_params(rng=(-25.6, -25.6, -3, 25.6, 25.6, 1), voxel=(0.4, 0.4, 4)):

@@ -156,6 +156,24 @@ def downsample_conv(x, sd: SD, p: str, cfg):
 # ---------------------------------------------------------------------------------------------
 # warp + fusion
 # ---------------------------------------------------------------------------------------------
+def convnext_aligner(x, sd: SD, p: str, num_blocks: int, kernel_size: int = 7):
+    """AlignNet(core_method='convnext') = ConvNeXt: `num_blocks` x ConvNeXtBlock
+    (feature_alignnet.py:12-39, feature_alignnet_modules.py:299-360; LayerNorm channels_last eps 1e-6 :12-25)."""
+    for i in range(num_blocks):
+        q = f"{p}.channel_align.model.{i}"
+        c = x.shape[1]
+        y = F.conv2d(x, sd[q + ".dwconv.weight"], sd[q + ".dwconv.bias"], padding=kernel_size // 2, groups=c)
+        y = y.permute(0, 2, 3, 1)
+        y = F.layer_norm(y, (c,), sd[q + ".norm.weight"], sd[q + ".norm.bias"], 1e-6)
+        y = F.linear(y, sd[q + ".pwconv1.weight"], sd[q + ".pwconv1.bias"])
+        y = F.gelu(y)
+        y = F.linear(y, sd[q + ".pwconv2.weight"], sd[q + ".pwconv2.bias"])
+        if (q + ".gamma") in sd:
+            y = sd[q + ".gamma"] * y
+        x = x + y.permute(0, 3, 1, 2)
+    return x
+
+
 def normalize_pairwise_tfm(pairwise_t_matrix, H, W, discrete_ratio, downsample_rate=1):
     """utils/transformation_utils.py:68-92."""
     a = pairwise_t_matrix[:, :, :, [0, 1], :][:, :, :, :, [0, 1, 3]].clone()
@@ -307,7 +325,11 @@ def heter_pyramid_collab(sd: SD, args, data_dict, encoder_fns=None):
         else:
             f = point_pillar_encoder(sd, f"encoder_{m}", args[m]["encoder_args"], data_dict[f"inputs_{m}"])
         f = resnet_bev_backbone(f, sd, f"backbone_{m}", args[m]["backbone_args"])
-        assert args[m]["aligner_args"]["core_method"] == "identity"
+        al = args[m]["aligner_args"]
+        if al["core_method"] == "convnext":
+            f = convnext_aligner(f, sd, f"aligner_{m}", al["args"]["num_of_blocks"], al["args"].get("kernel_size", 7))
+        else:
+            assert al["core_method"] == "identity"
         feats[m] = f
     counting = {m: 0 for m in mods}
     lst = []

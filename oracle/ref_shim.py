@@ -44,6 +44,10 @@ def install():
             m.__path__ = []  # behave as a package
             m.__spec__ = None
             sys.modules[name] = m
+    # heal_b200.install.install_into_opencood() aliases product modules under opencood.* names; the reference side must never
+    # resolve to them, so such aliases are dropped here and re-imported from the reference tree on demand
+    for k in [k for k, v in sys.modules.items() if k.startswith("opencood") and getattr(v, "__name__", k).startswith("heal_b200")]:
+        del sys.modules[k]
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     return REFERENCE_ROOT

@@ -23,6 +23,17 @@ from workloads import procedural
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _isolate_opencood_modules():
+    """install_into_opencood() aliases heal_b200 mirrors under `opencood.models.*` in sys.modules; other test modules import the
+    UNMODIFIED reference under those names (oracle.ref_runner), so everything opencood / shapely is restored afterwards."""
+    before = {k: v for k, v in sys.modules.items() if k.startswith(("opencood", "shapely"))}
+    yield
+    for k in [k for k in sys.modules if k.startswith(("opencood", "shapely"))]:
+        del sys.modules[k]
+    sys.modules.update(before)
+
+
 def _install_reference_with_quad_polygon():
     from unittest.mock import MagicMock
     sg = types.ModuleType("shapely.geometry")

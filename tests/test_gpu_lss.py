@@ -69,3 +69,84 @@ def test_lss_full_size_properties():
     torch.testing.assert_close(bev.sum((1, 2)), expect, rtol=2e-3, atol=2e-2)
     bev2 = ops.lss_pool(logits, 2 * feat, cell, N, 256, 256).t
     torch.testing.assert_close(bev2, 2 * bev, rtol=1e-4, atol=1e-4)   # linear in the features (atomics reorder only)
+
+
+def test_lss_pool_sorted_vs_golden_both_layouts_and_deterministic(golden_dir):
+    """heal_lss_pool_sorted (cell-sorted interval sums, no atomics): equals the exact per-cell sum, the unmodified reference's
+    cumsum output within its own rounding, for NCHW inputs and for the channels-last fused-heads layout, bit-identical run to run."""
+    from heal_b200 import ops
+    g = torch.load(os.path.join(golden_dir, "lss_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    fr = lss.create_frustum(cfg["grid_conf"], cfg["data_aug_conf"]["final_dim"], cfg["img_downsample"])
+    dx, bx, nx = lss.gen_dx_bx(cfg["grid_conf"]["xbound"], cfg["grid_conf"]["ybound"], cfg["grid_conf"]["zbound"])
+    B, N, _, _ = _mats(g)
+    D, fH, fW = fr.shape[:3]
+    C = g["feat"].shape[1]
+    HW = fH * fW
+    ref_cell = lss.cell_index(g["geom"], dx, bx, nx).view(B * N, D, fH, fW).int().cuda().contiguous()
+    x = lss.outer_product(g["depth_logits"], g["feat"]).view(B, N, -1, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    ref_exact = lss.voxel_pooling(g["geom"], x, dx, bx, nx, exact=True)
+    lg, ft = g["depth_logits"].cuda().contiguous(), g["feat"].cuda().contiguous()
+    a = ops.lss_pool_sorted(lg, (D * HW, HW, 1), ft, (C * HW, HW, 1), ref_cell, N, D, C, fH, fW, int(nx[0]), int(nx[1]))
+    got = ops.act_to_nchw(a).cpu().contiguous()
+    torch.testing.assert_close(got, ref_exact, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got, g["bev"], rtol=1e-3, atol=1e-3)
+    # channels-last fused heads: (BN, fH, fW, D + C)
+    fused = torch.cat([lg.permute(0, 2, 3, 1), ft.permute(0, 2, 3, 1)], -1).contiguous()
+    S = D + C
+    b = ops.lss_pool_sorted(fused, (HW * S, 1, S), fused[..., D:], (HW * S, 1, S), ref_cell, N, D, C, fH, fW, int(nx[0]), int(nx[1]))
+    assert torch.equal(b.t, a.t)                                      # same sums in the same order from either layout
+    for _ in range(3):
+        again = ops.lss_pool_sorted(lg, (D * HW, HW, 1), ft, (C * HW, HW, 1), ref_cell, N, D, C, fH, fW, int(nx[0]), int(nx[1]))
+        assert torch.equal(again.t, a.t)                              # deterministic, unlike the atomicAdd kernel
+    s = ops.lss_pool_sorted(lg, (D * HW, HW, 1), ft, (C * HW, HW, 1), ref_cell, N, D, C, fH, fW, int(nx[0]), int(nx[1]), out_fmt="split")
+    assert (ops.act_to_nchw(s).cpu() - got).abs().max().item() < 1e-4 * max(got.abs().max().item(), 1.0)
+
+
+def test_camera_trunk_on_the_conv_engine_vs_torch():
+    """CamEncode_Resnet101.heads_nhwc (space-to-depth stem on tcgen05, heal_maxpool3x3s2, Bottlenecks, fused heads) == the torch
+    modules' own forward (torchvision resnet101 conv1..layer2 + 1x1 heads, lss_submodule.py:140-233) on CPU."""
+    from heal_b200 import engine
+    from heal_b200.models.heter_encoders import CamEncode_Resnet101
+    from workloads import procedural
+    old = engine.PRECISION
+    try:
+        m = CamEncode_Resnet101(48, 128, 8, [2, 50, 48], "LID", False, False).eval()
+        m.load_state_dict(procedural.make_state_dict(procedural.shapes_of(m)), strict=True)
+        x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(2))
+        with torch.no_grad():
+            dl, ft = m.heads(x)
+        m = m.cuda()
+        for prec, tol in (("tc32", 1e-3), ("fp32", 1e-3), ("bf16", 1e-2)):
+            engine.set_precision(prec)
+            with torch.no_grad():
+                y = m.heads_nhwc(x.cuda()).t.cpu()
+            assert y.shape == (2, 8, 12, 48 + 128)
+            ref = torch.cat([dl, ft], 1).permute(0, 2, 3, 1)
+            err = (y - ref).abs().max().item()
+            scale = max(ref.abs().max().item(), 1.0)
+            print(f"camera trunk {prec}: max|ref|={scale:.3f} err={err:.3e}")
+            assert err <= tol * scale
+    finally:
+        engine.set_precision(old)
+
+
+def test_lift_splat_shoot_voxel_equals_lss_for_single_slice_grid():
+    """LiftSplatShootVoxel (heter_encoders.py:244-301) differs from LiftSplatShoot only in how z slices are merged (max vs concat);
+    with the single-slice grids of every HEAL yaml (zbound [-10, 10, 20]) both reduce to the same (B,C,ny,nx) map."""
+    from heal_b200 import synth
+    from heal_b200.models.heter_encoders import LiftSplatShoot, LiftSplatShootVoxel
+    from oracle import make_golden
+    from workloads import procedural
+    cfg = make_golden.lss_small_cfg()
+    a, b = LiftSplatShoot(dict(cfg)).eval(), LiftSplatShootVoxel(dict(cfg)).eval()
+    sd = procedural.make_state_dict(procedural.shapes_of(a))
+    a.load_state_dict(sd, strict=True)
+    b.load_state_dict(sd, strict=True)
+    a, b = a.cuda(), b.cuda()
+    rots, trans, intr, post_rots, post_trans = [torch.from_numpy(v).cuda() for v in synth.camera_rig(1, 2, 64, 128)]
+    imgs = torch.randn(1, 2, 3, 64, 128, generator=torch.Generator().manual_seed(8)).cuda()
+    dd = {"inputs_m2": {"imgs": imgs, "rots": rots, "trans": trans, "intrins": intr, "post_rots": post_rots, "post_trans": post_trans}}
+    with torch.no_grad():
+        ya, yb = a(dd, "m2"), b(dd, "m2")
+    assert ya.shape == (1, 32, 64, 64) and torch.equal(ya, yb)

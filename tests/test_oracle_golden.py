@@ -78,3 +78,13 @@ def test_heter_model_baseline_att_small(golden_dir):
         out = nets.heter_model_baseline(sd, g["args"], g["data"])
     for k in ("cls_preds", "reg_preds", "dir_preds"):
         torch.testing.assert_close(out[k], g["out"][k], rtol=1e-4, atol=1e-4)
+
+
+def test_convnext_aligner_oracle_vs_reference_golden(golden_dir):
+    """oracle.nets.convnext_aligner == the UNMODIFIED reference AlignNet(convnext) output (feature_alignnet_modules.py:299-360)."""
+    import os
+    g = torch.load(os.path.join(golden_dir, "convnext_aligner.pt"), weights_only=False)
+    sd = {"al." + k: v for k, v in procedural.make_state_dict(g["shapes"]).items()}
+    with torch.no_grad():
+        y = nets.convnext_aligner(g["x"], sd, "al", g["cfg"]["args"]["num_of_blocks"])
+    assert (y - g["y"]).abs().max().item() <= 1e-5
