@@ -25,7 +25,7 @@ SIGNATURES = {
     "heal_voxelize_workspace": (_sz, [_i, _i, _i]),
     "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _ap, _vp]),
+    "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _ap, _vp]),
     "heal_pillar_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ap, _vp]),
     "heal_pillar_idmap": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "heal_sparse_stem": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _ap, _ap, _vp]),
@@ -48,7 +48,9 @@ SIGNATURES = {
     "heal_spconv_strided_workspace": (_sz, [_i, _i, _i]),
     "heal_spconv_strided_rulebook": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_spconv_gather_gemm": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "heal_spconv_gather_gemm_tc": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "heal_spconv_gather_gemm_tc": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp,
+                                        _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_longlong, _vp]),
+    "heal_stem_rulebook": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "heal_rows_to_split": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "heal_sparse_to_bev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "heal_lss_cell_index": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

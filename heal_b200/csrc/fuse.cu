@@ -258,7 +258,8 @@ struct AttP {
     float inv_sqrt_dim;
 };
 
-// one warp per output pixel; lane covers channels {4*lane + 128*q}
+// one warp per output pixel; lane covers channels {4*lane + 128*q}.  Every agent's warped feature vector is sampled ONCE and
+// kept in registers for both the ego-row scores and the weighted sum (the first version sampled twice = 2x the HBM reads).
 template <int Q>
 __global__ void __launch_bounds__(256)
 k_att_fuse(AttP p) {
@@ -266,56 +267,51 @@ k_att_fuse(AttP p) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int pix = blockIdx.x * (blockDim.x >> 5) + warp;
     if (pix >= HW) return;
-    Tap taps[MAX_AGENTS];
-    for (int j = 0; j < p.n; ++j) taps[j] = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
-    auto sample = [&](int j, float4* x) {
-#pragma unroll
-        for (int q = 0; q < Q; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int off = taps[j].off[k];
-            if (off >= 0) {
-                float w = taps[j].w[k];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    float4 v = act_load4(p.feat, (size_t)j * HW + off, 4 * lane + 128 * q);
-                    x[q].x = fmaf(v.x, w, x[q].x); x[q].y = fmaf(v.y, w, x[q].y);
-                    x[q].z = fmaf(v.z, w, x[q].z); x[q].w = fmaf(v.w, w, x[q].w);
-                }
-            }
-        }
-    };
-    float4 x0[Q], xj[Q];
-    sample(0, x0);
+    float4 xs[MAX_AGENTS][Q];
     float sc[MAX_AGENTS];
     float mx = -INFINITY;
-    for (int j = 0; j < p.n; ++j) {
-        if (j == 0) {
 #pragma unroll
-            for (int q = 0; q < Q; ++q) xj[q] = x0[q];
-        } else sample(j, xj);
-        float d = 0.f;
+    for (int j = 0; j < MAX_AGENTS; ++j) {
+        if (j < p.n) {
+            const Tap t = make_tap(p.theta + 6 * j, pix / p.W, pix % p.W, p.H, p.W, p.align);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) d += x0[q].x * xj[q].x + x0[q].y * xj[q].y + x0[q].z * xj[q].z + x0[q].w * xj[q].w;
-        d = warp_sum(d) * p.inv_sqrt_dim;
-        sc[j] = d;
-        mx = fmaxf(mx, d);
+            for (int q = 0; q < Q; ++q) xs[j][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int off = t.off[k];
+                if (off >= 0) {
+                    const float w = t.w[k];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = act_load4(p.feat, (size_t)j * HW + off, 4 * lane + 128 * q);
+                        xs[j][q].x = fmaf(v.x, w, xs[j][q].x); xs[j][q].y = fmaf(v.y, w, xs[j][q].y);
+                        xs[j][q].z = fmaf(v.z, w, xs[j][q].z); xs[j][q].w = fmaf(v.w, w, xs[j][q].w);
+                    }
+                }
+            }
+            float d = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) d += xs[0][q].x * xs[j][q].x + xs[0][q].y * xs[j][q].y + xs[0][q].z * xs[j][q].z + xs[0][q].w * xs[j][q].w;
+            d = warp_sum(d) * p.inv_sqrt_dim;
+            sc[j] = d;
+            mx = fmaxf(mx, d);
+        }
     }
     float den = 0.f;
-    for (int j = 0; j < p.n; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+#pragma unroll
+    for (int j = 0; j < MAX_AGENTS; ++j) if (j < p.n) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
     float4 acc[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < p.n; ++j) {
-        float a = sc[j] / den;
-        if (j == 0) {
 #pragma unroll
-            for (int q = 0; q < Q; ++q) xj[q] = x0[q];
-        } else sample(j, xj);
+    for (int j = 0; j < MAX_AGENTS; ++j) {
+        if (j < p.n) {
+            const float a = sc[j] / den;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            acc[q].x = fmaf(a, xj[q].x, acc[q].x); acc[q].y = fmaf(a, xj[q].y, acc[q].y);
-            acc[q].z = fmaf(a, xj[q].z, acc[q].z); acc[q].w = fmaf(a, xj[q].w, acc[q].w);
+            for (int q = 0; q < Q; ++q) {
+                acc[q].x = fmaf(a, xs[j][q].x, acc[q].x); acc[q].y = fmaf(a, xs[j][q].y, acc[q].y);
+                acc[q].z = fmaf(a, xs[j][q].z, acc[q].z); acc[q].w = fmaf(a, xs[j][q].w, acc[q].w);
+            }
         }
     }
 #pragma unroll

@@ -128,70 +128,99 @@ __global__ void k_lss_keys(const int* __restrict__ cell, long long n, int DHW, i
     vals[i] = (int)i;
 }
 
-// softmax over D for every (image, pixel): one thread per pixel (D = 48: the logits of a pixel are contiguous for NHWC heads)
-__global__ void k_lss_prob(SortedP p) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// softmax over D for every (image, pixel): one warp per pixel, lanes over depth bins (D <= 64); probabilities are stored
+// pixel-major [image][pixel][D] so that both this kernel's writes and the pooling kernel's reads are contiguous per pixel
+__global__ void __launch_bounds__(256)
+k_lss_prob(SortedP p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 8 + warp;
     if (t >= (long long)p.BN * p.HW) return;
     const int bn = (int)(t / p.HW), pix = (int)(t % p.HW);
     const float* lg = p.logits + (long long)bn * p.l_img + (long long)pix * p.l_pix;
-    float mx = -INFINITY;
-    for (int d = 0; d < p.D; ++d) mx = fmaxf(mx, __ldg(lg + d * p.l_d));
-    float s = 0.f;
-    for (int d = 0; d < p.D; ++d) s += expf(__ldg(lg + d * p.l_d) - mx);
-    float* pr = p.prob + ((size_t)bn * p.D) * p.HW + pix;
-    for (int d = 0; d < p.D; ++d) pr[(size_t)d * p.HW] = expf(__ldg(lg + d * p.l_d) - mx) / s;
+    const float v0 = (lane < p.D) ? __ldg(lg + (long long)lane * p.l_d) : -INFINITY;
+    const float v1 = (lane + 32 < p.D) ? __ldg(lg + (long long)(lane + 32) * p.l_d) : -INFINITY;
+    float mx = fmaxf(v0, v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = (lane < p.D) ? expf(v0 - mx) : 0.f, e1 = (lane + 32 < p.D) ? expf(v1 - mx) : 0.f;
+    const float s = warp_sum(e0 + e1);
+    float* pr = p.prob + (size_t)t * p.D;
+    if (lane < p.D) pr[lane] = e0 / s;
+    if (lane + 32 < p.D) pr[lane + 32] = e1 / s;
 }
 
-__global__ void k_lss_starts(const unsigned* __restrict__ keys, long long n, unsigned total_cells, int* __restrict__ start) {
+__global__ void k_lss_hist(const unsigned* __restrict__ keys, long long n, unsigned total_cells, int* __restrict__ cnt) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = keys[i];
-    if (k < total_cells && (i == 0 || keys[i - 1] != k)) start[k] = (int)i;
+    if (k < total_cells) atomicAdd(&cnt[k], 1);        // integer counts: the result does not depend on the order of the atomics
 }
 
-// one warp per BEV cell; lane covers channels lane, lane+32, ... (C <= 256)
+// Interval pooling: a block owns LSS_G consecutive BEV cells = ONE contiguous interval of the sorted point list.  Thread = channel:
+// it walks the interval in order (ascending point id inside a cell: a fixed summation order), accumulates prob * feature and
+// writes each cell's value when the cell ends (empty cells get zeros: the whole map is written, no memset).  Point ids,
+// probabilities and feature row offsets are staged through shared memory 128 points at a time, so the per-point global reads
+// are one coalesced feature row (C x 4 B) with independent addresses.
+constexpr int LSS_G = 64;
+constexpr int LSS_TILE = 128;
+
 __global__ void __launch_bounds__(256)
-k_lss_pool_cells(SortedP p, const unsigned* __restrict__ keys, const int* __restrict__ vals, const int* __restrict__ start, long long n) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long cellg = (long long)blockIdx.x * 8 + warp;
-    const long long total = (long long)p.agents * p.cells_per_agent;
-    if (cellg >= total) return;
-    float acc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    const int s = start[cellg];
-    if (s >= 0) {
-        const int DHW = p.D * p.HW;
-        for (long long j = s; j < n && keys[j] == (unsigned)cellg; ++j) {
-            const int i = vals[j];
-            const int bn = i / DHW, pix = (i - bn * DHW) % p.HW;
-            const float pr = p.prob[i];
-            const float* f = p.feat + (long long)bn * p.f_img + (long long)pix * p.f_pix;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = q * 32 + lane;
-                if (c < p.C) acc[q] = fmaf(pr, __ldg(f + (long long)c * p.f_c), acc[q]);
+k_lss_pool_ranges(SortedP p, const int* __restrict__ vals, const int* __restrict__ offs, long long total_cells) {
+    __shared__ int s_off[LSS_G + 1];
+    __shared__ float s_pr[LSS_TILE];
+    __shared__ long long s_fo[LSS_TILE];
+    const long long c0 = (long long)blockIdx.x * LSS_G;
+    const int nc = (int)min((long long)LSS_G, total_cells - c0);
+    const int tid = threadIdx.x, ch = tid;
+    for (int i = tid; i <= nc; i += blockDim.x) s_off[i] = offs[c0 + i];
+    __syncthreads();
+    const int p0 = s_off[0], p1 = s_off[nc];
+    const int DHW = p.D * p.HW;
+    int cur = 0;                       // cell (block-local) being accumulated
+    int next_end = s_off[1];
+    float acc = 0.f;
+    const bool active = ch < p.C;
+    for (int base = p0; base < p1; base += LSS_TILE) {
+        const int n = min(LSS_TILE, p1 - base);
+        if (tid < n) {
+            const int i = vals[base + tid];
+            const int bn = i / DHW, rem = i - bn * DHW;
+            const int d = rem / p.HW, pix = rem - d * p.HW;
+            s_pr[tid] = p.prob[((size_t)bn * p.HW + pix) * p.D + d];
+            s_fo[tid] = (long long)bn * p.f_img + (long long)pix * p.f_pix;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int t = 0; t < n; ++t) {
+                const int j = base + t;
+                while (j >= next_end) {                     // the current cell is complete (also steps over empty cells)
+                    act_store1(p.out, (size_t)(c0 + cur), ch, acc);
+                    acc = 0.f; ++cur; next_end = s_off[cur + 1];
+                }
+                acc = fmaf(s_pr[t], __ldg(p.feat + s_fo[t] + (long long)ch * p.f_c), acc);
             }
         }
+        __syncthreads();
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int c = q * 32 + lane;
-        if (c < p.C) act_store1(p.out, (size_t)cellg, c, acc[q]);
+    if (active) {
+        for (; cur < nc; ++cur) { act_store1(p.out, (size_t)(c0 + cur), ch, acc); acc = 0.f; }
     }
 }
 
-struct SortedWs { size_t keys_in, keys_out, vals_in, vals_out, prob, start, cub, total, cub_bytes; };
+struct SortedWs { size_t keys_in, keys_out, vals_in, vals_out, prob, cnt, offs, cub, total, cub_bytes; };
 
 SortedWs sorted_layout(long long npts, long long total_cells, int end_bit) {
     SortedWs L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = heal_align_up(o + bytes, 256); return r; };
     L.keys_in = take(npts * 4); L.keys_out = take(npts * 4); L.vals_in = take(npts * 4); L.vals_out = take(npts * 4);
-    L.prob = take(npts * 4); L.start = take(total_cells * 4);
-    size_t tb = 0;
+    L.prob = take(npts * 4); L.cnt = take((total_cells + 1) * 4); L.offs = take((total_cells + 1) * 4);
+    size_t tb = 0, tb2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr,
                                     (int)npts, 0, end_bit);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, (const int*)nullptr, (int*)nullptr, (int)(total_cells + 1));
+    if (tb2 > tb) tb = tb2;
     L.cub_bytes = tb;
     L.cub = take(tb);
     L.total = o + 256;
@@ -231,16 +260,20 @@ extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, 
     p.out.p = bev_out->data; p.out.fmt = bev_out->fmt; p.out.cs = bev_out->cstride; p.out.co = bev_out->coffset; p.out.plane = bev_out->plane_stride;
     unsigned* k_in = (unsigned*)(ws + L.keys_in); unsigned* k_out = (unsigned*)(ws + L.keys_out);
     int* v_in = (int*)(ws + L.vals_in); int* v_out = (int*)(ws + L.vals_out);
-    int* start = (int*)(ws + L.start);
+    int* cnt = (int*)(ws + L.cnt); int* offs = (int*)(ws + L.offs);
+    if (D > 64) return HEAL_ERR_UNSUPPORTED;
     const unsigned gp = (unsigned)((npts + 255) / 256);
     k_lss_keys<<<gp, 256, 0, st>>>(cell, npts, D * fH * fW, cams_per_agent, cells_per_agent, (unsigned)cells, k_in, v_in);
-    k_lss_prob<<<(unsigned)(((long long)num_images * p.HW + 127) / 128), 128, 0, st>>>(p);
+    k_lss_prob<<<(unsigned)(((long long)num_images * p.HW + 7) / 8), 256, 0, st>>>(p);
     size_t tb = L.cub_bytes;
     if (cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, k_in, k_out, v_in, v_out, (int)npts, 0, bits, st) != cudaSuccess) return HEAL_ERR_LAUNCH;
-    cudaMemsetAsync(start, 0xFF, (size_t)cells * 4, st);
-    k_lss_starts<<<gp, 256, 0, st>>>(k_out, npts, (unsigned)cells, start);
-    k_lss_pool_cells<<<(unsigned)((cells + 7) / 8), 256, 0, st>>>(p, k_out, v_out, start, npts);
-    return heal_check_launch(6);
+    cudaMemsetAsync(cnt, 0, (size_t)(cells + 1) * 4, st);
+    k_lss_hist<<<gp, 256, 0, st>>>(k_in, npts, (unsigned)cells, cnt);
+    tb = L.cub_bytes;
+    if (cub::DeviceScan::ExclusiveSum(ws + L.cub, tb, cnt, offs, (int)(cells + 1), st) != cudaSuccess) return HEAL_ERR_LAUNCH;
+    const int threads = (C + 31) / 32 * 32 < 128 ? 128 : (C + 31) / 32 * 32;
+    k_lss_pool_ranges<<<(unsigned)((cells + LSS_G - 1) / LSS_G), threads, 0, st>>>(p, v_out, offs, cells);
+    return heal_check_launch(7);
 }
 
 extern "C" int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(PV_WARPS * 32)
 k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ num_points,
                      const int4* __restrict__ coords, const int* __restrict__ num_voxels_dev, int M,
                      const float* __restrict__ Wf, const float* __restrict__ bf, PvCfg c,
-                     float* __restrict__ pillar_out, ActV canvas) {
+                     float* __restrict__ pillar_out, __nv_bfloat16* __restrict__ pillar_split_out, ActV canvas) {
     __shared__ float sW[PV_CIN * PV_COUT];
     __shared__ float sB[PV_COUT];
     __shared__ __align__(16) float sF[PV_WARPS][32][12];
@@ -80,6 +80,13 @@ k_pillar_vfe_scatter(const float4* __restrict__ voxels, const int* __restrict__ 
     }
     float2 o = make_float2(m0, m1);
     if (pillar_out) reinterpret_cast<float2*>(pillar_out + (size_t)v * PV_COUT)[lane] = o;
+    if (pillar_split_out) {      // split rows [hi 64 | lo 64]: the gather source of the tensor-core sparse stem (heal_spconv_gather_gemm_tc)
+        __nv_bfloat16* r = pillar_split_out + (size_t)v * (2 * PV_COUT);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o.x, o.y);
+        const float2 hf = __bfloat1622float2(h);
+        reinterpret_cast<__nv_bfloat162*>(r)[lane] = h;
+        reinterpret_cast<__nv_bfloat162*>(r + PV_COUT)[lane] = __floats2bfloat162_rn(o.x - hf.x, o.y - hf.y);
+    }
     if (canvas.p) {
         size_t cell = ((size_t)cd.x * c.ny + (size_t)cd.z) * c.nx + (size_t)(cd.y + cd.w);  // z + y*nx + x, z == 0
         if (canvas.fmt == 0) {
@@ -129,7 +136,7 @@ extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* v
                                        const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
                                        const float* w_folded, const float* b_folded, int c_in, int c_out,
                                        const float* voxel_size3, const float* offset3, int nx, int ny,
-                                       float* pillar_features_out, const heal_act_t* canvas_out, void* stream_) {
+                                       float* pillar_features_out, void* pillar_split_rows_out, const heal_act_t* canvas_out, void* stream_) {
     if (!voxel_features || !voxel_num_points || !voxel_coords || !w_folded || !b_folded) return HEAL_ERR_ARG;
     if (c_in != PV_CIN || c_out != PV_COUT || max_points_per_voxel < 1 || max_points_per_voxel > 32) return HEAL_ERR_UNSUPPORTED;
     if (num_voxels <= 0) return HEAL_OK;
@@ -148,6 +155,6 @@ extern "C" int heal_pillar_vfe_scatter(const float* voxel_features, const int* v
     if (grid > HEAL_NUM_SMS * 8) grid = HEAL_NUM_SMS * 8;
     k_pillar_vfe_scatter<<<grid, PV_WARPS * 32, 0, (cudaStream_t)stream_>>>(
         (const float4*)voxel_features, voxel_num_points, (const int4*)voxel_coords, num_voxels_dev, num_voxels,
-        w_folded, b_folded, c, pillar_features_out, cv);
+        w_folded, b_folded, c, pillar_features_out, (__nv_bfloat16*)pillar_split_rows_out, cv);
     return heal_check_launch();
 }

@@ -30,7 +30,9 @@ constexpr int SPT_M = 128;
 constexpr int SPT_ATILE = SPT_M * 128;          // one plane of A: 128 rows x 128 B
 
 struct SptP {
-    const __nv_bfloat16* in;     // (rows_in, 2*CIN) split rows
+    const __nv_bfloat16* in;     // split rows: hi channels at in + row*in_pitch, lo channels at + in_lo (interleaved rows: pitch 2*CIN, lo CIN;
+                                 // a planar split `Act`: pitch = pixel stride, lo = plane stride)
+    long long in_pitch, in_lo, out_pitch, out_lo;
     const int* nbr;              // (capacity, K)
     const int* m_dev;            // live output rows on the device (or nullptr)
     int M;                       // capacity
@@ -134,11 +136,11 @@ k_spconv_tc(const __grid_constant__ CUtensorMap tmB, const SptP p) {
                 for (int it = 0; it < 8; ++it) {
                     const int r = warp * 32 + it * 4 + (lane >> 3);
                     const int src = (tap < p.K) ? snbr[r * KPAD + tap] : -1;
-                    const __nv_bfloat16* g = p.in + (src >= 0 ? (size_t)src * (2 * CIN) + sc * 8 : 0);
+                    const __nv_bfloat16* g = p.in + (src >= 0 ? (long long)src * p.in_pitch + sc * 8 : 0);
                     const uint32_t nb = src >= 0 ? 16u : 0u;
                     const uint32_t d = sa + r * 128 + ((c ^ (r & 7)) << 4);
                     cp_async16(d, g, nb);                            // hi plane
-                    cp_async16(d + SPT_ATILE, g + (src >= 0 ? CIN : 0), nb);   // lo plane
+                    cp_async16(d + SPT_ATILE, g + (src >= 0 ? p.in_lo : 0), nb);   // lo plane
                 }
                 cp_async_commit();
                 pend[npend++] = stage;
@@ -224,9 +226,9 @@ k_spconv_tc(const __grid_constant__ CUtensorMap tmB, const SptP p) {
                                 hw[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
                                 lw[j] = pack_bf16(v[2 * j] - h0, v[2 * j + 1] - h1);
                             }
-                            __nv_bfloat16* o = p.out_split + (size_t)grow * (2 * COUT) + c0 + g8 * 8;
+                            __nv_bfloat16* o = p.out_split + (long long)grow * p.out_pitch + c0 + g8 * 8;
                             *reinterpret_cast<uint4*>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            *reinterpret_cast<uint4*>(o + COUT) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            *reinterpret_cast<uint4*>(o + p.out_lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
                         if (p.out_f32) {
                             float* o = p.out_f32 + (size_t)grow * COUT + c0 + g8 * 8;
@@ -287,11 +289,34 @@ __global__ void k_rows_to_split(const float* __restrict__ in, const int* __restr
     out[(size_t)r * 2 * C + C + c] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// PointPillars stem as a sparse 2-D convolution: rulebook of a k x k / stride-2 conv from the pillar list (cell -> pillar row id
+// map) to the DENSE output grid.  nbr[(b*Ho + oy)*Wo + ox][r*k + s] = idmap[b][2oy + r - pad][2ox + s - pad] or -1.
+__global__ void k_stem_rulebook(const int* __restrict__ idmap, int B, int ny, int nx, int Ho, int Wo, int k, int pad, int* __restrict__ nbr) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = k * k;
+    if (t >= (long long)B * Ho * Wo * K) return;
+    const int tap = (int)(t % K);
+    long long pix = t / K;
+    const int ox = (int)(pix % Wo); pix /= Wo;
+    const int oy = (int)(pix % Ho); const int b = (int)(pix / Ho);
+    const int y = 2 * oy + tap / k - pad, x = 2 * ox + tap % k - pad;
+    nbr[t] = (y >= 0 && y < ny && x >= 0 && x < nx) ? __ldg(idmap + ((size_t)b * ny + y) * nx + x) : -1;
+}
+
 }  // namespace
+
+extern "C" int heal_stem_rulebook(const int* idmap, int batch, int ny, int nx, int ksize, int pad, int* nbr_out, void* stream_) {
+    if (!idmap || !nbr_out || batch < 1 || (ny & 1) || (nx & 1) || ksize < 1) return HEAL_ERR_ARG;
+    const int Ho = ny / 2, Wo = nx / 2;
+    const long long total = (long long)batch * Ho * Wo * ksize * ksize;
+    k_stem_rulebook<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(idmap, batch, ny, nx, Ho, Wo, ksize, pad, nbr_out);
+    return heal_check_launch();
+}
 
 extern "C" int heal_spconv_gather_gemm_tc(const void* in_split_rows, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,
                                           const void* w_packed, const float* bias, int c_in, int c_out, int relu,
-                                          void* out_split_rows, float* out_f32, void* stream_) {
+                                          void* out_split_rows, float* out_f32,
+                                          long long in_pitch, long long in_lo, long long out_pitch, long long out_lo, void* stream_) {
     if (!in_split_rows || !nbr || !w_packed || (!out_split_rows && !out_f32) || out_capacity < 1) return HEAL_ERR_ARG;
     if (kvol < 1 || kvol > 27) return HEAL_ERR_UNSUPPORTED;
     if (c_in != 16 && c_in != 32 && c_in != 64) return HEAL_ERR_UNSUPPORTED;
@@ -299,6 +324,9 @@ extern "C" int heal_spconv_gather_gemm_tc(const void* in_split_rows, const int* 
     p.in = (const __nv_bfloat16*)in_split_rows; p.nbr = nbr; p.m_dev = out_rows_dev; p.M = out_capacity;
     p.K = kvol; p.KB = (kvol + (64 / c_in) - 1) / (64 / c_in);
     p.bias = bias; p.relu = relu; p.out_split = (__nv_bfloat16*)out_split_rows; p.out_f32 = out_f32;
+    p.in_pitch = in_pitch > 0 ? in_pitch : 2 * c_in; p.in_lo = in_lo > 0 ? in_lo : c_in;
+    p.out_pitch = out_pitch > 0 ? out_pitch : 2 * c_out; p.out_lo = out_lo > 0 ? out_lo : c_out;
+    if ((p.in_pitch | p.in_lo | p.out_pitch | p.out_lo) & 7) return HEAL_ERR_UNSUPPORTED;      // 16-byte rows
     cudaStream_t st = (cudaStream_t)stream_;
 #define SPT(ci, co) if (c_in == ci && c_out == co) return launch_spt<ci, co>(p, w_packed, st)
     SPT(16, 16); SPT(16, 32); SPT(32, 32); SPT(32, 64); SPT(64, 64); SPT(64, 128);

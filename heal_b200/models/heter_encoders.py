@@ -56,7 +56,8 @@ class PointPillar(nn.Module):
         w, b = self.pillar_vfe.folded()
         if sparse:
             return ops.pillar_vfe_sparse(vf, vn, vc, w, b, self.voxel_size, self.lidar_range, nx=self.scatter.nx,
-                                         ny=self.scatter.ny, batch_size=batch_size, num_voxels_dev=nvox_dev)
+                                         ny=self.scatter.ny, batch_size=batch_size, num_voxels_dev=nvox_dev,
+                                         want_split_rows=(ops.STEM_GATHER_TC and fmt == "split"))
         _, canvas = ops.pillar_vfe_scatter(vf, vn, vc, w, b, self.voxel_size, self.lidar_range,
                                            nx=self.scatter.nx, ny=self.scatter.ny, batch_size=batch_size,
                                            num_voxels_dev=nvox_dev, canvas_fmt=fmt)

@@ -270,8 +270,9 @@ def fold_linear_bn(weight: torch.Tensor, bn_w, bn_b, bn_mean, bn_var, eps: float
 def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded,
                        voxel_size, lidar_range, nx: int, ny: int, batch_size: int,
                        want_pillar_features: bool = False, want_canvas: bool = True,
-                       num_voxels_dev: Optional[torch.Tensor] = None, canvas_fmt: str = "f32"):
-    """Returns (pillar_features (M,64) | None, canvas Act (B,ny,nx,64) in `canvas_fmt` | None)."""
+                       num_voxels_dev: Optional[torch.Tensor] = None, canvas_fmt: str = "f32", split_rows_out: Optional[torch.Tensor] = None):
+    """Returns (pillar_features (M,64) | None, canvas Act (B,ny,nx,64) in `canvas_fmt` | None).  `split_rows_out`: optional
+    (M,128) bf16 buffer that receives the pillar features as split rows [hi | lo] (tensor-core sparse stem input)."""
     _need_cuda(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded)
     M, T, C = voxel_features.shape
     assert C == 4
@@ -304,7 +305,7 @@ def pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded,
             cview = ctypes.byref(cv)
         rc = lib.heal_pillar_vfe_scatter(_p(vf), _p(npts), _p(coords), _p(num_voxels_dev), M, T,
                                          _p(w_folded), _p(b_folded), w_folded.shape[0], cout,
-                                         _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), cview, _stream())
+                                         _host_f32(vs), _host_f32(off), int(nx), int(ny), _p(pf), _p(split_rows_out), cview, _stream())
     check(rc, "heal_pillar_vfe_scatter")
     return pf, canvas
 
@@ -747,7 +748,7 @@ def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
     return nbr
 
 
-SP_GROWTH = 2.0     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
+SP_GROWTH = 1.5     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
 
 
 def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int] = None):
@@ -763,7 +764,7 @@ def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int]
         for i in range(3):
             fan *= -(-ksize[i] // stride[i])
         out_capacity = int(min(st.capacity * fan, st.batch * oshape[0] * oshape[1] * oshape[2],
-                               max(int(st.capacity * SP_GROWTH), 1024)))
+                               max(int(st.capacity * SP_GROWTH), 1024), 1 << 20))        # 2^20 rows: the rulebook scan's limit
     dev = st.coords.device
     ts = lib.heal_spconv_table_size(out_capacity)
     okeys = torch.empty((ts,), dtype=torch.int32, device=dev)
@@ -851,7 +852,8 @@ def sp_gather_gemm_tc(feats_split: torch.Tensor, nbr: torch.Tensor, rows_dev, w_
     with _Prof("spconv_gather_gemm_tc", lambda: 2.0 * _pairs()[0] * cin * cout,
                lambda: _pairs()[0] * (cin * 4.0 + 4.0) + _pairs()[1] * (cout * 4.0 + K * 4.0)):
         rc = lib.heal_spconv_gather_gemm_tc(_p(feats_split), _p(nbr), _p(rows_dev), cap, K, _p(w_packed), _p(bias), cin, cout,
-                                            1 if relu else 0, _vp(0) if want_f32 else _p(out), _p(out) if want_f32 else _vp(0), _stream())
+                                            1 if relu else 0, _vp(0) if want_f32 else _p(out), _p(out) if want_f32 else _vp(0),
+                                            0, 0, 0, 0, _stream())
     check(rc, "heal_spconv_gather_gemm_tc")
     return out
 
@@ -874,8 +876,8 @@ class SparseCanvas:
     """Stands for the (B, ny, nx, 64) scatter canvas: pillar features + a cell -> pillar-row map.  `dense(fmt)` materialises
     the canvas for consumers that need it; the first stride-2 residual block consumes it directly (heal_sparse_stem)."""
 
-    def __init__(self, feats, idmap, B, ny, nx, densify):
-        self.feats, self.idmap = feats, idmap
+    def __init__(self, feats, idmap, B, ny, nx, densify, feats_split=None):
+        self.feats, self.idmap, self.feats_split = feats, idmap, feats_split
         self.N, self.H, self.W, self.C = B, ny, nx, feats.shape[1]
         self._densify = densify
         self.fmt = "sparse"
@@ -889,10 +891,14 @@ class SparseCanvas:
 
 
 def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded, voxel_size, lidar_range,
-                      nx: int, ny: int, batch_size: int, num_voxels_dev: Optional[torch.Tensor] = None) -> SparseCanvas:
-    """PillarVFE -> pillar features (M,64) + id map; no dense canvas."""
+                      nx: int, ny: int, batch_size: int, num_voxels_dev: Optional[torch.Tensor] = None,
+                      want_split_rows: bool = False) -> SparseCanvas:
+    """PillarVFE -> pillar features (M,64) (+ the same as split rows) + id map; no dense canvas."""
+    fsplit = torch.empty((voxel_features.shape[0], 2 * w_folded.shape[1]), dtype=torch.bfloat16, device=voxel_features.device) \
+        if want_split_rows else None
     pf, _ = pillar_vfe_scatter(voxel_features, voxel_num_points, voxel_coords, w_folded, b_folded, voxel_size, lidar_range,
-                               nx, ny, batch_size, want_pillar_features=True, want_canvas=False, num_voxels_dev=num_voxels_dev)
+                               nx, ny, batch_size, want_pillar_features=True, want_canvas=False, num_voxels_dev=num_voxels_dev,
+                               split_rows_out=fsplit)
     coords = voxel_coords.to(torch.int32).contiguous()
     idmap = torch.empty((batch_size, ny, nx), dtype=torch.int32, device=pf.device)
     with _Prof("pillar_idmap", 0, batch_size * float(ny) * nx * 4 + coords.shape[0] * 16.0):
@@ -904,7 +910,39 @@ def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, 
                                        lidar_range, nx, ny, batch_size, num_voxels_dev=num_voxels_dev, canvas_fmt=fmt)
         return canvas
 
-    return SparseCanvas(pf, idmap, batch_size, ny, nx, densify)
+    return SparseCanvas(pf, idmap, batch_size, ny, nx, densify, feats_split=fsplit)
+
+
+STEM_GATHER_TC = True     # tc32 mode: the stem as two tcgen05 gather-GEMMs (heal_spconv_gather_gemm_tc) instead of k_sparse_stem
+
+
+def _sparse_stem_gather_tc(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, o1: Act, o2: Act):
+    """The first stride-2 residual block's 3x3 conv and 1x1 downsample as sparse 2-D convolutions on the tensor cores: a rulebook
+    (output pixel x kernel offset -> pillar row, from the cell->row id map) + the SECOND encoder's gather-GEMM kernel, which reads
+    the pillar list's split rows and writes straight into the dense BEV maps (planar split Acts).  Only offsets that hit a pillar
+    somewhere in a 128-pixel tile cost an MMA; empty tiles cost one."""
+    B, Ho, Wo = sc.N, sc.H // 2, sc.W // 2
+    rows = B * Ho * Wo
+    dev = sc.device
+    for pc in (pc_conv, pc_down):
+        if getattr(pc, "_sp_packed", None) is None or pc._sp_packed.device != dev:
+            K = pc.kh * pc.kw
+            pc._sp_packed = pack_spconv_tc(pc.weight.reshape(K, pc.cin, pc.w_cstride)[:, :, :pc.cout].contiguous())
+    nbr9 = torch.empty((rows, 9), dtype=torch.int32, device=dev)
+    nbr1 = torch.empty((rows, 1), dtype=torch.int32, device=dev)
+    with _Prof("sparse_stem_rulebook", 0, rows * 40.0 + B * float(sc.H) * sc.W * 4):
+        check(lib.heal_stem_rulebook(_p(sc.idmap), B, sc.H, sc.W, 3, 1, _p(nbr9), _stream()), "heal_stem_rulebook")
+        check(lib.heal_stem_rulebook(_p(sc.idmap), B, sc.H, sc.W, 1, 0, _p(nbr1), _stream()), "heal_stem_rulebook")
+
+    def _hits():
+        return float((sc.idmap >= 0).sum().item())
+    with _Prof("sparse_stem_tc", lambda: 2.0 * 64 * 64 * (2.25 + 0.25) * _hits(),
+               lambda: rows * 40.0 + _hits() * 2.5 * 256.0 + 2.0 * rows * 64 * 4):
+        for nbr, pc, o, relu in ((nbr9, pc_conv, o1, 1), (nbr1, pc_down, o2, 0)):
+            rc = lib.heal_spconv_gather_gemm_tc(_p(sc.feats_split), _p(nbr), _vp(0), rows, nbr.shape[1], _p(pc._sp_packed), _p(pc.bias), 64, 64,
+                                                relu, _p(o.t), _vp(0), 0, 0, o.cstride, o.plane_stride, _stream())
+            check(rc, "heal_spconv_gather_gemm_tc")
+    return o1, o2
 
 
 def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_fmt: str, tensor_cores: bool = False):
@@ -914,6 +952,8 @@ def sparse_stem(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, out_
     assert pc_down.kh == 1 and pc_down.stride == 2 and pc_down.pad == 0 and pc_down.cin == 64 and pc_down.cout == 64 and not pc_down.relu
     o1 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
     o2 = act_empty(sc.N, sc.H // 2, sc.W // 2, 64, out_fmt, sc.device)
+    if STEM_GATHER_TC and out_fmt == "split" and sc.feats_split is not None:
+        return _sparse_stem_gather_tc(sc, pc_conv, pc_down, o1, o2)
     v1, v2 = o1.view(), o2.view()
     fn = lib.heal_sparse_stem_tc if (tensor_cores and sc.W % 32 == 0) else lib.heal_sparse_stem
     def _stem():

@@ -73,14 +73,15 @@ int heal_mean_vfe(const float* voxels, const int* num_points, int num_voxels, in
  * and PointPillarScatter.forward (opencood/models/sub_modules/point_pillar_scatter.py:19-77).
  *   w_folded (10,64) = linear.weight^T * bn_scale, b_folded (64) = bn_shift (folded on the host, fp64)
  *   offset3_host = voxel_size/2 + range_min (x,y,z)
- *   pillar_features_out (M,64) fp32 or NULL; canvas_out: (B,ny,nx,64) channels-last view in any storage
+ *   pillar_features_out (M,64) fp32 or NULL; pillar_split_rows_out (M,128) bf16 [hi 64 | lo 64] or NULL (the gather source of
+ *   the tensor-core sparse stem); canvas_out: (B,ny,nx,64) channels-last view in any storage
  *   format, pre-zeroed by the caller, or NULL
  *   num_voxels_dev: optional device count (row 0 used) so a graph-captured frame needs no host sync */
 int heal_pillar_vfe_scatter(const float* voxel_features, const int* voxel_num_points, const int* voxel_coords,
                             const int* num_voxels_dev, int num_voxels, int max_points_per_voxel,
                             const float* w_folded, const float* b_folded, int c_in, int c_out,
                             const float* voxel_size3_host, const float* offset3_host, int nx, int ny,
-                            float* pillar_features_out, const heal_act_t* canvas_out, void* stream);
+                            float* pillar_features_out, void* pillar_split_rows_out, const heal_act_t* canvas_out, void* stream);
 
 /* Stand-alone PointPillarScatter.forward (opencood/models/sub_modules/point_pillar_scatter.py:19-77): rows of pillar features
  * (M,channels) f32 -> canvas cell [b][y][x + z] of a pre-zeroed channels-last canvas view (any storage format). */
@@ -231,10 +232,17 @@ int heal_spconv_gather_gemm(const float* in_feats, const int* nbr, const int* ou
  * 128B-swizzled K-major tiles, TMA weight tiles), for c_in in {16,32,64}.  Features are "split rows": (rows, 2*C) bf16 =
  * [hi C | lo C] with x ~= hi + lo; products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation (fp32-equivalent).
  *   w_packed   [2 planes][KB * c_out rows][64] bf16, KB = ceil(kvol / (64 / c_in)); column = (offset within K-block) * c_in + ci
- *   out_split_rows (capacity, 2*c_out) bf16 and / or out_f32 (capacity, c_out) */
+ *   out_split_rows (capacity, 2*c_out) bf16 and / or out_f32 (capacity, c_out)
+ *   in_pitch / in_lo / out_pitch / out_lo (elements; 0 = the interleaved-row defaults 2C / C): row pitch and hi->lo distance, so
+ *   that the kernel can also gather from / write to a PLANAR split activation (pitch = pixel stride, lo = plane stride) -- used
+ *   by the PointPillars sparse stem, whose outputs are dense BEV maps in the conv engine's format. */
 int heal_spconv_gather_gemm_tc(const void* in_split_rows, const int* nbr, const int* out_rows_dev, int out_capacity, int kvol,
                                const void* w_packed, const float* bias, int c_in, int c_out, int relu,
-                               void* out_split_rows, float* out_f32, void* stream);
+                               void* out_split_rows, float* out_f32,
+                               long long in_pitch, long long in_lo, long long out_pitch, long long out_lo, void* stream);
+/* Rulebook of a ksize x ksize / stride-2 2-D convolution from the pillar list to the dense (batch, ny/2, nx/2) output grid:
+ * nbr_out[(b*Ho + oy)*Wo + ox][r*ksize + s] = idmap[b][2oy + r - pad][2ox + s - pad] or -1 (idmap: heal_pillar_idmap). */
+int heal_stem_rulebook(const int* idmap, int batch, int ny, int nx, int ksize, int pad, int* nbr_out, void* stream);
 /* fp32 rows (capacity, C) -> split rows (capacity, 2*C) bf16 */
 int heal_rows_to_split(const float* rows_f32, const int* rows_dev, int capacity, int channels, void* out_split_rows, void* stream);
 int heal_sparse_to_bev(const float* feats, const int* coords, const int* rows_dev, int capacity, int C, int D, int H, int W,

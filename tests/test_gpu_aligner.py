@@ -19,7 +19,7 @@ def _restore_precision():
     engine.set_precision(old)
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tc32", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tc32", 1e-3), ("bf16", 2.5e-2)])
 def test_convnext_aligner_vs_reference_golden(golden_dir, prec, tol):
     from heal_b200 import engine
     from heal_b200.models.sub_modules.feature_alignnet import AlignNet

@@ -251,7 +251,8 @@ def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
         blk.load_state_dict(blk_sd, strict=True)
         blk = blk.cuda()
         args = (col["voxel_features"], col["voxel_num_points"], col["voxel_coords"], w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2)
-        sparse = ops.pillar_vfe_sparse(*args)
+        # tc32 (default engine path): PillarVFE also emits split rows and the stem runs as two tcgen05 gather-GEMMs
+        sparse = ops.pillar_vfe_sparse(*args, want_split_rows=(prec == "tc32" and not engine.STEM_TC))
         _, dense = ops.pillar_vfe_scatter(*args, canvas_fmt=engine.act_fmt())
         with torch.no_grad():
             a = ops.act_to_nchw(blk.forward_nhwc(sparse)).cpu()

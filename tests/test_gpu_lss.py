@@ -117,7 +117,7 @@ def test_camera_trunk_on_the_conv_engine_vs_torch():
         with torch.no_grad():
             dl, ft = m.heads(x)
         m = m.cuda()
-        for prec, tol in (("tc32", 1e-3), ("fp32", 1e-3), ("bf16", 1e-2)):
+        for prec, tol in (("tc32", 1e-3), ("fp32", 1e-3), ("bf16", 2.5e-2)):
             engine.set_precision(prec)
             with torch.no_grad():
                 y = m.heads_nhwc(x.cuda()).t.cpu()

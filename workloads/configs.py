@@ -11,6 +11,8 @@ yaml sources (relative to the reference root, opencood/hypes_yaml/opv2v/MoreModa
 """
 import copy
 
+import numpy as np
+
 RANGE = [-102.4, -102.4, -3, 102.4, 102.4, 1]          # inference.py:34 / lidar_attfuse.yaml:17
 CAM_RANGE = [-51.2, -51.2, -3, 51.2, 51.2, 1]
 PILLAR_VOXEL = [0.4, 0.4, 4]
@@ -45,6 +47,8 @@ def pyramid_backbone_args():
 def c1_args(rng=RANGE):
     """models/point_pillar.py single agent."""
     a = pillar_encoder_args(rng)
+    # yaml_utils.load_point_pillar_params (hypes_yaml/yaml_utils.py:121-135) writes the grid size into the scatter args
+    a["point_pillar_scatter"]["grid_size"] = np.round((np.array(rng[3:6]) - np.array(rng[0:3])) / np.array(PILLAR_VOXEL)).astype(np.int64)
     a.update({"anchor_number": 2,
               "base_bev_backbone": {"layer_nums": [3, 5, 8], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
                                     "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]},
