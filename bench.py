@@ -911,7 +911,7 @@ def postprocess_leg(wl, frame_dev):
             pp._decode_one(cav, heads)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             pp._decode_one(cav, heads)
         g.replay()
         torch.cuda.synchronize()

@@ -149,78 +149,95 @@ k_lss_prob(SortedP p) {
     if (lane + 32 < p.D) pr[lane + 32] = e1 / s;
 }
 
-__global__ void k_lss_hist(const unsigned* __restrict__ keys, long long n, unsigned total_cells, int* __restrict__ cnt) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned k = keys[i];
-    if (k < total_cells) atomicAdd(&cnt[k], 1);        // integer counts: the result does not depend on the order of the atomics
-}
-
-// Interval pooling: a block owns LSS_G consecutive BEV cells = ONE contiguous interval of the sorted point list.  Thread = channel:
-// it walks the interval in order (ascending point id inside a cell: a fixed summation order), accumulates prob * feature and
-// writes each cell's value when the cell ends (empty cells get zeros: the whole map is written, no memset).  Point ids,
-// probabilities and feature row offsets are staged through shared memory 128 points at a time, so the per-point global reads
-// are one coalesced feature row (C x 4 B) with independent addresses.
-constexpr int LSS_G = 64;
-constexpr int LSS_TILE = 128;
+// Balanced interval pooling.  The sorted point list is cut into chunks of LSS_CH points, one block per chunk, thread = channel.
+// (BEV cells next to the cameras collect hundreds of frustum points, cells far away one or two: a cell-per-warp or cells-per-block
+// split leaves a few blocks with 10^4 sequential iterations; equal point counts per block do not.)  A thread walks its chunk in
+// order; a cell that begins AND ends inside the chunk is written straight to the (pre-zeroed) BEV map; the partial sum of a cell
+// that crosses a chunk boundary goes to part[chunk][0 = head (cell began earlier) | 1 = tail (cell continues)].  k_lss_pool_fixup
+// then adds, for every cell with a tail partial, the head partials of the following chunks in chunk order.  Summation order is
+// fixed (ascending point id, grouped by chunk): bit-identical from run to run.
+constexpr int LSS_CH = 128;
+constexpr unsigned LSS_NONE = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256)
-k_lss_pool_ranges(SortedP p, const int* __restrict__ vals, const int* __restrict__ offs, long long total_cells) {
-    __shared__ int s_off[LSS_G + 1];
-    __shared__ float s_pr[LSS_TILE];
-    __shared__ long long s_fo[LSS_TILE];
-    const long long c0 = (long long)blockIdx.x * LSS_G;
-    const int nc = (int)min((long long)LSS_G, total_cells - c0);
+k_lss_pool_chunks(SortedP p, const unsigned* __restrict__ keys, const int* __restrict__ vals, long long n, unsigned total_cells,
+                  float* __restrict__ part, unsigned* __restrict__ pkey) {
+    __shared__ unsigned s_key[LSS_CH];
+    __shared__ float s_pr[LSS_CH];
+    __shared__ long long s_fo[LSS_CH];
+    __shared__ unsigned s_edge[2];
+    const long long base = (long long)blockIdx.x * LSS_CH;
     const int tid = threadIdx.x, ch = tid;
-    for (int i = tid; i <= nc; i += blockDim.x) s_off[i] = offs[c0 + i];
-    __syncthreads();
-    const int p0 = s_off[0], p1 = s_off[nc];
     const int DHW = p.D * p.HW;
-    int cur = 0;                       // cell (block-local) being accumulated
-    int next_end = s_off[1];
-    float acc = 0.f;
-    const bool active = ch < p.C;
-    for (int base = p0; base < p1; base += LSS_TILE) {
-        const int n = min(LSS_TILE, p1 - base);
-        if (tid < n) {
-            const int i = vals[base + tid];
+    if (tid < LSS_CH) {
+        const long long j = base + tid;
+        unsigned k = (j < n) ? keys[j] : LSS_NONE;
+        if (k >= total_cells) k = LSS_NONE;
+        s_key[tid] = k;
+        if (k != LSS_NONE) {
+            const int i = vals[j];
             const int bn = i / DHW, rem = i - bn * DHW;
             const int d = rem / p.HW, pix = rem - d * p.HW;
             s_pr[tid] = p.prob[((size_t)bn * p.HW + pix) * p.D + d];
             s_fo[tid] = (long long)bn * p.f_img + (long long)pix * p.f_pix;
         }
-        __syncthreads();
-        if (active) {
-#pragma unroll 4
-            for (int t = 0; t < n; ++t) {
-                const int j = base + t;
-                while (j >= next_end) {                     // the current cell is complete (also steps over empty cells)
-                    act_store1(p.out, (size_t)(c0 + cur), ch, acc);
-                    acc = 0.f; ++cur; next_end = s_off[cur + 1];
-                }
-                acc = fmaf(s_pr[t], __ldg(p.feat + s_fo[t] + (long long)ch * p.f_c), acc);
-            }
-        }
-        __syncthreads();
     }
-    if (active) {
-        for (; cur < nc; ++cur) { act_store1(p.out, (size_t)(c0 + cur), ch, acc); acc = 0.f; }
+    if (tid == 0) {
+        s_edge[0] = (base > 0) ? keys[base - 1] : LSS_NONE;
+        unsigned nx = (base + LSS_CH < n) ? keys[base + LSS_CH] : LSS_NONE;
+        s_edge[1] = (nx >= total_cells) ? LSS_NONE : nx;
+    }
+    __syncthreads();
+    if (ch >= p.C) return;
+    unsigned cur = s_key[0];
+    if (cur == LSS_NONE) return;                       // the whole chunk lies in the invalid tail
+    bool started_here = (s_edge[0] != cur);
+    float acc = 0.f;
+    float* mypart = part + (size_t)blockIdx.x * 2 * p.C;
+    int t = 0;
+#pragma unroll 4
+    for (; t < LSS_CH; ++t) {
+        const unsigned k = s_key[t];
+        if (k == LSS_NONE) break;
+        if (k != cur) {                                // the cell `cur` ended inside this chunk
+            if (started_here) act_store1(p.out, (size_t)cur, ch, acc);
+            else { mypart[ch] = acc; if (ch == 0) pkey[2 * blockIdx.x] = cur; }
+            acc = 0.f; cur = k; started_here = true;
+        }
+        acc = fmaf(s_pr[t], __ldg(p.feat + s_fo[t] + (long long)ch * p.f_c), acc);
+    }
+    const unsigned nextk = (t < LSS_CH) ? LSS_NONE : s_edge[1];
+    const bool ended_here = (nextk != cur);
+    if (started_here && ended_here) act_store1(p.out, (size_t)cur, ch, acc);
+    else {
+        const int slot = started_here ? 1 : 0;         // tail partial (cell continues) | head partial (also: a cell covering the whole chunk)
+        mypart[slot * p.C + ch] = acc;
+        if (ch == 0) pkey[2 * blockIdx.x + slot] = cur;
     }
 }
 
-struct SortedWs { size_t keys_in, keys_out, vals_in, vals_out, prob, cnt, offs, cub, total, cub_bytes; };
+__global__ void __launch_bounds__(256)
+k_lss_pool_fixup(SortedP p, const float* __restrict__ part, const unsigned* __restrict__ pkey, int nchunks) {
+    const int b = blockIdx.x, ch = threadIdx.x;
+    const unsigned key = pkey[2 * b + 1];
+    if (key == LSS_NONE || ch >= p.C) return;
+    float acc = part[((size_t)b * 2 + 1) * p.C + ch];
+    for (int b2 = b + 1; b2 < nchunks && pkey[2 * b2] == key; ++b2) acc += part[(size_t)b2 * 2 * p.C + ch];
+    act_store1(p.out, (size_t)key, ch, acc);
+}
 
-SortedWs sorted_layout(long long npts, long long total_cells, int end_bit) {
+struct SortedWs { size_t keys_in, keys_out, vals_in, vals_out, prob, part, pkey, cub, total, cub_bytes; };
+
+SortedWs sorted_layout(long long npts, long long total_cells, int end_bit, int C) {
     SortedWs L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = heal_align_up(o + bytes, 256); return r; };
     L.keys_in = take(npts * 4); L.keys_out = take(npts * 4); L.vals_in = take(npts * 4); L.vals_out = take(npts * 4);
-    L.prob = take(npts * 4); L.cnt = take((total_cells + 1) * 4); L.offs = take((total_cells + 1) * 4);
-    size_t tb = 0, tb2 = 0;
+    const long long nchunks = (npts + LSS_CH - 1) / LSS_CH;
+    L.prob = take(npts * 4); L.part = take((size_t)nchunks * 2 * C * 4); L.pkey = take((size_t)nchunks * 2 * 4);
+    size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr,
                                     (int)npts, 0, end_bit);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, (const int*)nullptr, (int*)nullptr, (int)(total_cells + 1));
-    if (tb2 > tb) tb = tb2;
     L.cub_bytes = tb;
     L.cub = take(tb);
     L.total = o + 256;
@@ -234,7 +251,7 @@ int key_bits(long long total_cells) { int b = 1; while ((1LL << b) <= total_cell
 extern "C" size_t heal_lss_pool_sorted_workspace(int num_images, int D, int fH, int fW, int agents, int cells_per_agent) {
     const long long npts = (long long)num_images * D * fH * fW, cells = (long long)agents * cells_per_agent;
     if (npts <= 0 || cells <= 0 || npts >= (1LL << 31)) return 0;
-    return sorted_layout(npts, cells, key_bits(cells)).total;
+    return sorted_layout(npts, cells, key_bits(cells), 256).total;
 }
 
 extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, long long l_d, long long l_pix,
@@ -248,7 +265,7 @@ extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, 
     const long long npts = (long long)num_images * D * fH * fW, cells = (long long)agents * cells_per_agent;
     if (npts >= (1LL << 31) || cells >= (1LL << 31)) return HEAL_ERR_UNSUPPORTED;
     const int bits = key_bits(cells);
-    SortedWs L = sorted_layout(npts, cells, bits);
+    SortedWs L = sorted_layout(npts, cells, bits, 256);
     if (workspace_bytes < L.total) return HEAL_ERR_WORKSPACE;
     char* ws = (char*)workspace;
     cudaStream_t st = (cudaStream_t)stream_;
@@ -260,20 +277,19 @@ extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, 
     p.out.p = bev_out->data; p.out.fmt = bev_out->fmt; p.out.cs = bev_out->cstride; p.out.co = bev_out->coffset; p.out.plane = bev_out->plane_stride;
     unsigned* k_in = (unsigned*)(ws + L.keys_in); unsigned* k_out = (unsigned*)(ws + L.keys_out);
     int* v_in = (int*)(ws + L.vals_in); int* v_out = (int*)(ws + L.vals_out);
-    int* cnt = (int*)(ws + L.cnt); int* offs = (int*)(ws + L.offs);
+    float* part = (float*)(ws + L.part); unsigned* pkey = (unsigned*)(ws + L.pkey);
+    const int nchunks = (int)((npts + LSS_CH - 1) / LSS_CH);
     if (D > 64) return HEAL_ERR_UNSUPPORTED;
     const unsigned gp = (unsigned)((npts + 255) / 256);
     k_lss_keys<<<gp, 256, 0, st>>>(cell, npts, D * fH * fW, cams_per_agent, cells_per_agent, (unsigned)cells, k_in, v_in);
     k_lss_prob<<<(unsigned)(((long long)num_images * p.HW + 7) / 8), 256, 0, st>>>(p);
     size_t tb = L.cub_bytes;
     if (cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, k_in, k_out, v_in, v_out, (int)npts, 0, bits, st) != cudaSuccess) return HEAL_ERR_LAUNCH;
-    cudaMemsetAsync(cnt, 0, (size_t)(cells + 1) * 4, st);
-    k_lss_hist<<<gp, 256, 0, st>>>(k_in, npts, (unsigned)cells, cnt);
-    tb = L.cub_bytes;
-    if (cub::DeviceScan::ExclusiveSum(ws + L.cub, tb, cnt, offs, (int)(cells + 1), st) != cudaSuccess) return HEAL_ERR_LAUNCH;
-    const int threads = (C + 31) / 32 * 32 < 128 ? 128 : (C + 31) / 32 * 32;
-    k_lss_pool_ranges<<<(unsigned)((cells + LSS_G - 1) / LSS_G), threads, 0, st>>>(p, v_out, offs, cells);
-    return heal_check_launch(7);
+    cudaMemsetAsync(pkey, 0xFF, (size_t)nchunks * 2 * 4, st);
+    const int threads = (C + 31) / 32 * 32 < LSS_CH ? LSS_CH : (C + 31) / 32 * 32;
+    k_lss_pool_chunks<<<nchunks, threads, 0, st>>>(p, k_out, v_out, npts, (unsigned)cells, part, pkey);
+    k_lss_pool_fixup<<<nchunks, threads, 0, st>>>(p, part, pkey, nchunks);
+    return heal_check_launch(6);
 }
 
 extern "C" int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,

@@ -32,7 +32,7 @@ class GraphedCall:
         torch.cuda.synchronize(device)
         self.graph = torch.cuda.CUDAGraph()
         l0 = lib.heal_launch_count()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = fn(self.data)
         self.kernels_per_replay = int(lib.heal_launch_count() - l0)
 
@@ -76,7 +76,7 @@ class FrameGraph:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         l0 = lib.heal_launch_count()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = fn(self.data)
         self.kernels_per_replay = int(lib.heal_launch_count() - l0)
 

@@ -680,12 +680,13 @@ def lss_pool_sorted(logits: torch.Tensor, l_strides, feat: torch.Tensor, f_strid
                     D: int, C: int, fH: int, fW: int, nx: int, ny: int, out_fmt: str = "f32") -> Act:
     """Deterministic LSS pooling (heal_lss_pool_sorted).  `logits` / `feat` are fp32 tensors whose data_ptr is the first logit /
     feature element, described by ELEMENT strides (image, depth-bin | channel, pixel); cell (BN,D,fH,fW) i32.
-    Returns Act (agents, ny, nx, C) in `out_fmt` (written completely: no memset)."""
+    Returns Act (agents, ny, nx, C) in `out_fmt` (zero where no frustum point lands)."""
     _need_cuda(logits, feat, cell)
     assert logits.dtype == torch.float32 and feat.dtype == torch.float32 and cell.dtype == torch.int32 and cell.is_contiguous()
     BN = cell.shape[0]
     agents = BN // cams_per_agent
     out = act_empty(agents, ny, nx, C, out_fmt, feat.device)
+    out.t.zero_()                                   # all-zero bits are 0.0 in every storage format; the kernel writes hit cells only
     wsb = lib.heal_lss_pool_sorted_workspace(BN, D, fH, fW, agents, nx * ny)
     ws = _workspace(feat.device, wsb)
     ov = out.view()
@@ -748,7 +749,7 @@ def sp_subm_neighbors(st: SparseTensor, ksize) -> torch.Tensor:
     return nbr
 
 
-SP_GROWTH = 1.5     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
+SP_GROWTH = 2.0     # default output-row capacity of a strided sparse conv relative to its input capacity (see sp_strided)
 
 
 def sp_strided(st: SparseTensor, ksize, stride, pad, out_capacity: Optional[int] = None):
@@ -913,7 +914,10 @@ def pillar_vfe_sparse(voxel_features, voxel_num_points, voxel_coords, w_folded, 
     return SparseCanvas(pf, idmap, batch_size, ny, nx, densify, feats_split=fsplit)
 
 
-STEM_GATHER_TC = True     # tc32 mode: the stem as two tcgen05 gather-GEMMs (heal_spconv_gather_gemm_tc) instead of k_sparse_stem
+# The stem as two tcgen05 gather-GEMMs (heal_stem_rulebook + heal_spconv_gather_gemm_tc with planar I/O) instead of k_sparse_stem.
+# Correct and tested, but measured SLOWER on the C2 frame (0.36 ms vs 0.20 ms: 2 560 output tiles x up to 9 K-blocks of mostly
+# zero-filled rows, weights re-streamed per tile) -> opt-in; the fp32 gather kernel stays the default.
+STEM_GATHER_TC = False
 
 
 def _sparse_stem_gather_tc(sc: SparseCanvas, pc_conv: PackedConv, pc_down: PackedConv, o1: Act, o2: Act):

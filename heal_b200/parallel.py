@@ -266,7 +266,7 @@ class AgentShardedFrame:
             dist.barrier(group=group)
         self.graph = torch.cuda.CUDAGraph()
         l0 = lib.heal_launch_count()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = self._frame()
         self.kernels_per_replay = int(lib.heal_launch_count() - l0)
 

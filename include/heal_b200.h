@@ -188,9 +188,11 @@ int heal_lss_pool(const float* depth_logits, const float* feat, const int* cell,
                   int D, int C, int fH, int fW, int cells_per_agent, float* bev_out, void* stream);
 
 /* Deterministic variant of heal_lss_pool (the default path): cell-sorted interval reduction, no atomics.  Points are radix-sorted
- * (stable, CUB) by agent*cells + cell; one warp per BEV cell sums prob * feature over the cell's interval in ascending point
- * order and writes the cell's channels once -- every run gives the same bits (the reference's QuickCumsum,
- * opencood/utils/camera_utils.py:220-246, is likewise a sum over a sorted interval).  No memset of the BEV map.
+ * (stable, CUB) by agent*cells + cell; the sorted list is cut into equal chunks of 128 points (one block each, thread = channel):
+ * cells inside a chunk are summed in ascending point order and written directly, cells crossing chunk boundaries are combined
+ * from per-chunk partial sums in chunk order -- a fixed summation order, every run gives the same bits (the reference's
+ * QuickCumsum, opencood/utils/camera_utils.py:220-246, is likewise a sum over a sorted interval).  bev_out must be PRE-ZEROED
+ * (cells no frustum point falls into are not written).
  *   depth_logits / feat with ELEMENT strides (image, depth-bin | channel, pixel): NCHW torch tensors (HW*D, HW, 1) or the
  *   channels-last output of the fused 1x1 heads (HW*S, 1, S).  bev_out: (agents, cells_per_agent, C) channels-last view, any format. */
 size_t heal_lss_pool_sorted_workspace(int num_images, int D, int fH, int fW, int agents, int cells_per_agent);

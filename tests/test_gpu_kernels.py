@@ -227,13 +227,14 @@ def test_warp_att_golden(golden_dir):
     torch.testing.assert_close(ops.act_to_nchw(out)[0].cpu().contiguous(), g["att"][0], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tc32", "tc32-mma"])
+@pytest.mark.parametrize("prec", ["fp32", "tc32", "tc32-mma", "tc32-gather"])
 def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
     """scatter + first residual block straight from the pillar list == the same block on the materialised canvas == the oracle."""
     from heal_b200 import ops, synth, engine
     from heal_b200.models.sub_modules.resblock import BasicBlock, conv1x1
     from oracle import procedural
-    old, old_tc = engine.PRECISION, engine.STEM_TC
+    old, old_tc, old_gather = engine.PRECISION, engine.STEM_TC, ops.STEM_GATHER_TC
+    ops.STEM_GATHER_TC = (prec == "tc32-gather")   # opt-in tcgen05 gather-GEMM stem (stem rulebook + heal_spconv_gather_gemm_tc)
     engine.STEM_TC = prec.endswith("-mma")          # heal_sparse_stem_tc (mma.sync, split-bf16) instead of the fp32 gather kernel
     prec = prec.split("-")[0]
     engine.set_precision(prec)
@@ -252,7 +253,7 @@ def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
         blk = blk.cuda()
         args = (col["voxel_features"], col["voxel_num_points"], col["voxel_coords"], w.cuda(), b.cuda(), PP_VOXEL, PP_RANGE, 512, 512, 2)
         # tc32 (default engine path): PillarVFE also emits split rows and the stem runs as two tcgen05 gather-GEMMs
-        sparse = ops.pillar_vfe_sparse(*args, want_split_rows=(prec == "tc32" and not engine.STEM_TC))
+        sparse = ops.pillar_vfe_sparse(*args, want_split_rows=ops.STEM_GATHER_TC)
         _, dense = ops.pillar_vfe_scatter(*args, canvas_fmt=engine.act_fmt())
         with torch.no_grad():
             a = ops.act_to_nchw(blk.forward_nhwc(sparse)).cpu()
@@ -277,4 +278,5 @@ def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
     finally:
         engine.SPARSE_STEM = True
         engine.STEM_TC = old_tc
+        ops.STEM_GATHER_TC = old_gather
         engine.set_precision(old)
