@@ -581,12 +581,17 @@ def run_gpu(opt):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: everything else written to fd 1 (NCCL prints its version banner and, with
+    # NCCL_DEBUG=INFO, its communicator log there) is sent to stderr for the whole run; the line goes out through the saved fd
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import datetime
-        # NCCL's INFO lines (communicator init: ranks, NVLS / NVLink transports) go to STDERR; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        # leave NCCL's INFO init lines (ranks per communicator, NVLS / NVLink transports) visible on stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("HEAL_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.pop("NCCL_DEBUG_FILE", None)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     from heal_b200._lib import lib
     from heal_b200 import ops
@@ -831,8 +836,8 @@ def run_gpu(opt):
                 "postprocess": post, "other_workloads": secondary,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "gflop_per_frame": frame_flops(n_agents) / 1e9 if is_pyramid_lidar else None}
-        print(json.dumps(line))
         sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     if rc:
