@@ -947,7 +947,8 @@ def agent_sharded_leg(opt, rank, world, dev, peaks):
     wl = GpuWorkload(wname, opt.precision, dev, n_agents=n_agents, scenes=scenes)
     steps = max(opt.steps, 10)
     with torch.no_grad():
-        sf = parallel.AgentShardedFrame(wl.model, n_agents, rank, world, wl.cap, scenes[0]["pairwise"].shape, device=dev)
+        sf = parallel.AgentShardedFrame(wl.model, n_agents, rank, world, wl.cap, scenes[0]["pairwise"].shape, device=dev,
+                                        comm=os.environ.get("HEAL_SHARD_COMM", "auto"))
         for i in range(3):
             sf.load_scene(wl.devin[i % 4]["points"], scenes[i % 4]["offsets"], wl.devin[i % 4]["pairwise"])
             sf.replay()
@@ -1002,11 +1003,13 @@ def agent_sharded_leg(opt, rank, world, dev, peaks):
             "frame_ms": lat, "frames_per_s": 1e3 / lat, "e2e_frames_per_s": steps / (ms_e2e / 1e3),
             "single_gpu_frame_ms_rank0": ref_ms, "speedup_vs_single_gpu": (ref_ms / lat) if ref_ms else None,
             "max_abs_diff_vs_single_gpu": equal,
-            "allgather": {"ms": ag_ms, "bytes_per_rank": ag["bytes_per_rank"], "bytes_received_per_rank": recv,
+            "allgather": {"comm": sf.comm, "ms": ag_ms, "bytes_per_rank": ag["bytes_per_rank"], "bytes_received_per_rank": recv,
                           "gbs_received_per_rank": recv / 1e9 / (ag_ms / 1e3) if ag_ms > 0 else None,
-                          "collectives_per_frame": sf.collectives_per_frame,
-                          "note": "ncclAllGather of the packed per-agent pyramids (in place, symmetric buffer), timed alone with CUDA "
-                                  "events, max over ranks; `bytes_received` = (ranks-1) x message"},
+                          "exchanges_per_frame": sf.exchanges_per_frame, "nccl_collectives_per_frame": sf.collectives_per_frame,
+                          "note": "exchange of the packed per-agent BEV pyramids through the symmetric buffer, timed ALONE (no compute to "
+                                  "overlap with) with CUDA events, max over ranks: comm='p2p' = heal_p2p_push of every level to all peers "
+                                  "over NVLink + one flag barrier (inside the frame the pushes run on a side stream under the next "
+                                  "level's convolutions); comm='nccl' = one in-place ncclAllGather.  `bytes_received` = (ranks-1) x message"},
             "tail": sf.tail_mode, "graph": True, "kernels_per_replay": sf.kernels_per_replay}
 
 

@@ -17,6 +17,14 @@
 namespace {
 
 constexpr uint32_t SP_EMPTY = 0xFFFFFFFFu;
+// Every kernel below loops over the LIVE rows (device count) with a grid-stride loop and is launched with a machine-sized grid:
+// row capacities are worst-case bounds (2x per strided level), the live counts are a fraction of them, and a capacity-sized
+// grid spent most of its blocks on an early exit (HeightCompression: 64 M threads for 3 M elements).
+constexpr int SP_MAX_BLOCKS = HEAL_NUM_SMS * 16;
+inline unsigned sp_grid(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    return (unsigned)(b < 1 ? 1 : (b > SP_MAX_BLOCKS ? SP_MAX_BLOCKS : b));
+}
 constexpr int SP_SCAN = 1024;
 
 struct SpGeom {
@@ -41,18 +49,18 @@ __device__ __forceinline__ int sp_lookup(const uint32_t* __restrict__ keys, cons
 
 __global__ void k_sp_build(const int4* __restrict__ coords, const int* __restrict__ m_dev, int M, SpGeom g,
                            uint32_t* __restrict__ keys, int* __restrict__ vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (i >= Md) return;
-    int4 c = coords[i];
-    uint32_t key = sp_key(c.x, c.y, c.z, c.w, g);
-    uint32_t s = sp_hash(key, g);
-    while (true) {
-        uint32_t prev = atomicCAS(&keys[s], SP_EMPTY, key);
-        if (prev == SP_EMPTY || prev == key) break;
-        s = (s + 1) & g.tmask;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Md; i += gridDim.x * blockDim.x) {
+        int4 c = coords[i];
+        uint32_t key = sp_key(c.x, c.y, c.z, c.w, g);
+        uint32_t s = sp_hash(key, g);
+        while (true) {
+            uint32_t prev = atomicCAS(&keys[s], SP_EMPTY, key);
+            if (prev == SP_EMPTY || prev == key) break;
+            s = (s + 1) & g.tmask;
+        }
+        vals[s] = i;
     }
-    vals[s] = i;
 }
 
 struct KShape { int kz, ky, kx, sz, sy, sx, pz, py, px; };
@@ -61,25 +69,26 @@ struct KShape { int kz, ky, kx, sz, sy, sx, pz, py, px; };
 __global__ void k_sp_subm_nbr(const int4* __restrict__ coords, const int* __restrict__ m_dev, int M, SpGeom g, KShape ks,
                               const uint32_t* __restrict__ keys, const int* __restrict__ vals, int* __restrict__ nbr) {
     const int K = ks.kz * ks.ky * ks.kx;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (t >= (long long)Md * K) return;
-    int i = (int)(t / K), k = (int)(t % K);
-    int dz = k / (ks.ky * ks.kx), dy = (k / ks.kx) % ks.ky, dx = k % ks.kx;
-    int4 c = coords[i];
-    int z = c.y + dz - ks.kz / 2, y = c.z + dy - ks.ky / 2, x = c.w + dx - ks.kx / 2;
-    int r = -1;
-    if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) r = sp_lookup(keys, vals, sp_key(c.x, z, y, x, g), g);
-    nbr[t] = r;
+    const long long total = (long long)Md * K, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int i = (int)(t / K), k = (int)(t % K);
+        int dz = k / (ks.ky * ks.kx), dy = (k / ks.kx) % ks.ky, dx = k % ks.kx;
+        int4 c = coords[i];
+        int z = c.y + dz - ks.kz / 2, y = c.z + dy - ks.ky / 2, x = c.w + dx - ks.kx / 2;
+        int r = -1;
+        if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) r = sp_lookup(keys, vals, sp_key(c.x, z, y, x, g), g);
+        nbr[t] = r;
+    }
 }
 
 // strided conv, pass 1: each (input i, offset k) proposes an output site; the smallest proposer id wins the site
 __global__ void k_sp_propose(const int4* __restrict__ coords, const int* __restrict__ m_dev, int M, SpGeom go, KShape ks,
                              uint32_t* __restrict__ okeys, int* __restrict__ ofirst, int* __restrict__ cand_slot, int* __restrict__ overflow) {
     const int K = ks.kz * ks.ky * ks.kx;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (t >= (long long)Md * K) return;
+    const long long total = (long long)Md * K, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     int i = (int)(t / K), k = (int)(t % K);
     int dz = k / (ks.ky * ks.kx), dy = (k / ks.kx) % ks.ky, dx = k % ks.kx;
     int4 c = coords[i];
@@ -107,18 +116,19 @@ __global__ void k_sp_propose(const int4* __restrict__ coords, const int* __restr
         }
     }
     cand_slot[t] = slot;
+    }
 }
 
 // pass 2: per input row, number of output sites it generates first (<= K)
 __global__ void k_sp_count_first(const int* __restrict__ m_dev, int M, int K, const int* __restrict__ ofirst,
                                  const int* __restrict__ cand_slot, int* __restrict__ cnt) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    int n = 0;
-    if (i < Md)
-        for (int k = 0; k < K; ++k) { int s = cand_slot[(size_t)i * K + k]; n += (s >= 0 && ofirst[s] == i * K + k) ? 1 : 0; }
-    cnt[i] = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {      // the scan reads all M entries
+        int n = 0;
+        if (i < Md)
+            for (int k = 0; k < K; ++k) { int s = cand_slot[(size_t)i * K + k]; n += (s >= 0 && ofirst[s] == i * K + k) ? 1 : 0; }
+        cnt[i] = n;
+    }
 }
 
 __global__ void k_sp_scan_local(const int* __restrict__ in, int n, int* __restrict__ local_excl, int* __restrict__ block_sums) {
@@ -168,9 +178,8 @@ __global__ void k_sp_assign(const int4* __restrict__ coords, const int* __restri
                             const int* __restrict__ local_excl, const int* __restrict__ block_off, int cap,
                             int* __restrict__ ovals, int4* __restrict__ out_coords) {
     const int K = ks.kz * ks.ky * ks.kx;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (i >= Md) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Md; i += gridDim.x * blockDim.x) {
     int rank = local_excl[i] + block_off[i / SP_SCAN];
     for (int k = 0; k < K; ++k) {
         int s = cand_slot[(size_t)i * K + k];
@@ -186,6 +195,7 @@ __global__ void k_sp_assign(const int4* __restrict__ coords, const int* __restri
             ++rank;
         }
     }
+    }
 }
 
 // a full hash table dropped candidates: report more rows than the capacity so that callers see the overflow
@@ -196,13 +206,14 @@ __global__ void k_sp_flag_overflow(const int* __restrict__ overflow, int cap, in
 // pass 4: nbr[out_row][k] = i
 __global__ void k_sp_link(const int* __restrict__ m_dev, int M, int K, const int* __restrict__ cand_slot,
                           const int* __restrict__ ovals, int* __restrict__ nbr) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (t >= (long long)Md * K) return;
-    int s = cand_slot[t];
-    if (s < 0) return;
-    int r = ovals[s];
-    if (r >= 0) nbr[(size_t)r * K + (t % K)] = (int)(t / K);
+    const long long total = (long long)Md * K, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int s = cand_slot[t];
+        if (s < 0) continue;
+        int r = ovals[s];
+        if (r >= 0) nbr[(size_t)r * K + (t % K)] = (int)(t / K);
+    }
 }
 
 // ---- gather-GEMM: out[r][:] = act(bias + sum_k in[nbr[r][k]][:] . W[k]) ------------------------------
@@ -263,13 +274,14 @@ k_sp_gather_gemm(const float* __restrict__ in, const int* __restrict__ nbr, cons
 // HeightCompression: dense (B, C*D, H, W) channels-last; channel index = c*D + z
 __global__ void k_sp_to_bev(const float* __restrict__ feats, const int4* __restrict__ coords, const int* __restrict__ m_dev, int M,
                             int C, int D, int H, int W, float* __restrict__ out) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int Md = m_dev ? min(M, m_dev[0]) : M;
-    if (t >= (long long)Md * C) return;
-    int i = (int)(t / C), c = (int)(t % C);
-    int4 cd = coords[i];
-    if (cd.y < 0 || cd.y >= D || cd.z < 0 || cd.z >= H || cd.w < 0 || cd.w >= W) return;
-    out[(((size_t)cd.x * H + cd.z) * W + cd.w) * (size_t)(C * D) + (size_t)c * D + cd.y] = feats[t];
+    const long long total = (long long)Md * C, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int i = (int)(t / C), c = (int)(t % C);
+        int4 cd = coords[i];
+        if (cd.y < 0 || cd.y >= D || cd.z < 0 || cd.z >= H || cd.w < 0 || cd.w >= W) continue;
+        out[(((size_t)cd.x * H + cd.z) * W + cd.w) * (size_t)(C * D) + (size_t)c * D + cd.y] = feats[t];
+    }
 }
 
 int table_log2(int n) { int lg = 10; while ((1 << lg) < 2 * n) ++lg; return lg; }
@@ -297,7 +309,7 @@ extern "C" int heal_spconv_build_table(const int* coords, const int* num_rows_de
     SpGeom g = make_geom(spatial_shape3_host, lg);
     size_t ts = (size_t)1 << lg;
     cudaMemsetAsync(table_keys, 0xFF, ts * 4, st);
-    k_sp_build<<<(capacity + 255) / 256, 256, 0, st>>>((const int4*)coords, num_rows_dev, capacity, g, table_keys, table_vals);
+    k_sp_build<<<sp_grid(capacity, 256), 256, 0, st>>>((const int4*)coords, num_rows_dev, capacity, g, table_keys, table_vals);
     return heal_check_launch(1);
 }
 
@@ -310,7 +322,7 @@ extern "C" int heal_spconv_subm_neighbors(const int* coords, const int* num_rows
     int K = ks.kz * ks.ky * ks.kx;
     SpGeom g = make_geom(spatial_shape3_host, table_log2(table_capacity));
     long long total = (long long)capacity * K;
-    k_sp_subm_nbr<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)coords, num_rows_dev, capacity, g, ks,
+    k_sp_subm_nbr<<<sp_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)coords, num_rows_dev, capacity, g, ks,
                                                                                      table_keys, table_vals, nbr_out);
     return heal_check_launch();
 }
@@ -356,7 +368,7 @@ extern "C" int heal_spconv_strided_rulebook(const int* in_coords, const int* in_
     cudaMemsetAsync(ofirst, 0x7F, ts * 4, st);
     cudaMemsetAsync(nbr_out, 0xFF, (size_t)out_capacity * K * 4, st);
     long long total = (long long)in_capacity * K;
-    unsigned gt = (unsigned)((total + 255) / 256), gm = (unsigned)((in_capacity + 255) / 256);
+    unsigned gt = sp_grid(total, 256), gm = sp_grid(in_capacity, 256);
     k_sp_propose<<<gt, 256, 0, st>>>((const int4*)in_coords, in_rows_dev, in_capacity, go, ks, out_table_keys, ofirst, cand_slot, overflow);
     k_sp_count_first<<<gm, 256, 0, st>>>(in_rows_dev, in_capacity, K, ofirst, cand_slot, cnt);
     k_sp_scan_local<<<nb, SP_SCAN, 0, st>>>(cnt, in_capacity, local_excl, block_off);
@@ -383,6 +395,6 @@ extern "C" int heal_sparse_to_bev(const float* feats, const int* coords, const i
                                   float* bev_out, void* stream_) {
     if (!feats || !coords || !bev_out || capacity < 1) return HEAL_ERR_ARG;
     long long total = (long long)capacity * C;
-    k_sp_to_bev<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(feats, (const int4*)coords, rows_dev, capacity, C, D, H, W, bev_out);
+    k_sp_to_bev<<<sp_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>(feats, (const int4*)coords, rows_dev, capacity, C, D, H, W, bev_out);
     return heal_check_launch();
 }

@@ -285,6 +285,15 @@ int heal_dwconv_layernorm(const heal_act_t* in, int N, int H, int W, int C, cons
  * (N,H/2,W/2,4C) with channel block (y&1)*2+(x&1) -- the phase-major output of the space-to-depth form of the 7x7/2 stem conv. */
 int heal_maxpool3x3s2(const heal_act_t* in, int N, int H, int W, int C, int depth_to_space_in, const heal_act_t* out, void* stream);
 
+/* ---- peer-to-peer exchange over NVLink / NVSwitch (agent-per-GPU partition) ---------------------
+ * The buffers are SYMMETRIC: every rank allocated the same size and mapped every peer's copy (peer_*_host[r] = this process's
+ * device pointer to rank r's copy; [self] = the local one).
+ * heal_p2p_push: copy `bytes` (multiple of 16) from src_local to peer_dst_host[r] for every r != self (same offset everywhere).
+ * heal_p2p_signal_wait: ++seq_dev[0]; store it (release, system scope) into flags[self] of every rank's flag array
+ *   (world u32 each); wait until the local flag array holds >= that value for every rank.  One thread block; capturable. */
+int heal_p2p_push(const void* src_local, void* const* peer_dst_host, int world, int self, size_t bytes, void* stream);
+int heal_p2p_signal_wait(void* const* peer_flags_host, int world, int self, unsigned* seq_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

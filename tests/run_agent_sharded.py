@@ -48,16 +48,19 @@ def main():
                 "agent_modality_list": ["m1"] * n_agents, "record_len": torch.tensor([n_agents]), "pairwise_t_matrix": pw}
         with torch.no_grad():
             ref = model(data)
-            for shard_tail in (True, False):
-                sf = parallel.AgentShardedFrame(model, n_agents, rank, world, 1 << 16, tuple(pw.shape), shard_tail=shard_tail)
-                sf.load_scene(pts, offs, pw)
-                out = sf.replay()
-                torch.cuda.synchronize()
-                for k in ("cls_preds", "reg_preds", "dir_preds"):
-                    same = torch.equal(ref[k], out[k])
-                    ok = ok and same
-                    if not same:
-                        print(f"rank {rank} graph agents {n_agents} shard_tail={shard_tail} {k}: max diff {(ref[k]-out[k]).abs().max().item():.3e}")
+            for comm, shard_tail in (("p2p", True), ("p2p", False), ("nccl", True), ("nccl", False)):
+                sf = parallel.AgentShardedFrame(model, n_agents, rank, world, 1 << 16, tuple(pw.shape), shard_tail=shard_tail, comm=comm)
+                for rep in range(3):                       # p2p mode alternates between two captured graphs / gather buffers
+                    sf.load_scene(pts, offs, pw)
+                    out = sf.replay()
+                    torch.cuda.synchronize()
+                    for k in ("cls_preds", "reg_preds", "dir_preds"):
+                        same = torch.equal(ref[k], out[k])
+                        ok = ok and same
+                        if not same:
+                            print(f"rank {rank} graph agents {n_agents} comm={comm} shard_tail={shard_tail} rep {rep} {k}: "
+                                  f"max diff {(ref[k]-out[k]).abs().max().item():.3e}")
+                dist.barrier()
                 del sf
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
