@@ -314,7 +314,7 @@ class AgentShardedFrame:
                     t = mychunk[fo:fo + planes * S * h * w * c * 2].view(torch.bfloat16).view(planes, S, h, w, c)
                 level_out.append(ops.Act(t, fmt))
                 occ_out.append(ops.Act(mychunk[oo:oo + S * h * w * 4].view(torch.float32).view(S, h, w, 1), "f32"))
-            self.sides.append({"gather": g, "level_out": level_out, "occ_out": occ_out})
+            self.sides.append({"i": len(self.sides), "gather": g, "level_out": level_out, "occ_out": occ_out})
         # static inputs: my agents' points (idle slots = empty clouds), their offsets, the scene's pairwise matrix
         self.cap = point_capacity
         self.points = torch.zeros((point_capacity, 4), dtype=torch.float32, device=dev)
@@ -398,7 +398,7 @@ class AgentShardedFrame:
         model, m = self.model, self.m
         pb = model.pyramid_backbone
         p2p = self.sym is not None
-        side_i = self.sides.index(sd)
+        side_i = sd["i"]
         enc, bb = getattr(model, f"encoder_{m}"), getattr(model, f"backbone_{m}")
         sub = {f'inputs_{m}': {'points': self.points, 'agent_offsets': self.offsets}}
         x = enc.forward_act(sub, m)
