@@ -71,7 +71,9 @@ struct TcP {
 // STG = number of 64-channel output staging buffers in shared memory (0: the epilogue stores straight to global memory;
 // >0: it writes the swizzled tile to smem and one elected thread issues a TMA tensor store, so every global write is a
 // full coalesced line and the drain is asynchronous).
-template <int BLOCK_N, int STAGES, int STG>
+// GELU: the exact-erf GELU epilogue (ConvNeXt pwconv1) lives in its OWN instantiations: this kernel is sensitive to code size
+// (an erff call inside every instantiation's epilogue cost the ReLU paths ~4 % of the C2 frame, A/B on the bench)
+template <int BLOCK_N, int STAGES, int STG, bool GELU = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcP p) {
@@ -420,12 +422,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += __ldg(rp + j);
                         }
-                        if (p.relu == 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (p.relu == 2) {
+                        if constexpr (GELU) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = heal_act_fn(v[j], 2);
+                        } else if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                         }
                         float lo[8];
 #pragma unroll
@@ -496,12 +498,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float* rp = p.res_f32 + pix * p.res_cs + p.res_co + c;
                             for (int j = 0; j < 8 && c + j < p.Cout; ++j) v[j] += __ldg(rp + j);
                         }
-                        if (p.relu == 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (p.relu == 2) {
+                        if constexpr (GELU) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = heal_act_fn(v[j], 2);
+                        } else if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                         }
                         if (p.out_split && !((p.dbg & 1) && v[0] != 1.2345e30f)) {
                             __nv_bfloat16* op = p.out_split + pix * p.out_cs + p.out_co + c;
@@ -562,7 +564,7 @@ struct TcEnv {
 };
 const TcEnv& tc_env() { static const TcEnv e; return e; }
 
-template <int BLOCK_N, int STAGES, int STG>
+template <int BLOCK_N, int STAGES, int STG, bool GELU = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const TcP& p_in, cudaStream_t st) {
     TcP p = p_in;
     p.res_tma = ((STG == 3 || (STG == 2 && BLOCK_N == 64 && STAGES == 2)) && p.tma_out && p.res_split && p_in.res_tma) ? 1 : 0;
@@ -572,7 +574,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     size_t smem = (size_t)STAGES * stage_bytes + (size_t)STG * p.planes * A_TILE_BYTES + 256;
     if (smem > 227 * 1024) return HEAL_ERR_UNSUPPORTED;
     static size_t attr_set[HEAL_MAX_DEVICES] = {};
-    if (!heal_ensure_dyn_smem(k_conv2d_tc<BLOCK_N, STAGES, STG>, 227 * 1024, attr_set)) return HEAL_ERR_LAUNCH;
+    if (!heal_ensure_dyn_smem(k_conv2d_tc<BLOCK_N, STAGES, STG, GELU>, 227 * 1024, attr_set)) return HEAL_ERR_LAUNCH;
     int total = p.m_tiles * p.n_tiles;
     int grid = total < HEAL_NUM_SMS ? total : HEAL_NUM_SMS;
     if (grid < 1) return HEAL_ERR_UNSUPPORTED;
@@ -583,11 +585,11 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv2d_tc<BLOCK_N, STAGES, STG>, tmA, tmB, tmO, tmR, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv2d_tc<BLOCK_N, STAGES, STG, GELU>, tmA, tmB, tmO, tmR, p);
         heal_launch_counter_add(1);
         return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
     }
-    k_conv2d_tc<BLOCK_N, STAGES, STG><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, tmR, p);
+    k_conv2d_tc<BLOCK_N, STAGES, STG, GELU><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmO, tmR, p);
     return heal_check_launch();
 }
 
@@ -751,6 +753,11 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     if (p.halo && p.bdiag) p.res_tma = 0;      // <64,4,1>: register prefetch
     cudaStream_t st = (cudaStream_t)stream_;
     const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
+    if (relu == 2) {        // GELU: 1x1 / 3x3 convs with >= 128 output channels and no residual (ConvNeXt pwconv1: dim -> 4 dim)
+        if (block_n != 128 || res_split || res_f32) return HEAL_ERR_UNSUPPORTED;
+        if (!p.tma_out) return launch_tc<128, 3, 0, true>(tmA, tmB, tmO, tmR, p, st);
+        return kblocks <= 4 ? launch_tc<128, 2, 2, true>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1, true>(tmA, tmB, tmO, tmR, p, st);
+    }
     switch (block_n) {
         case 16: return launch_tc<16, 4, 0>(tmA, tmB, tmO, tmR, p, st);
         case 32: return launch_tc<32, 4, 0>(tmA, tmB, tmO, tmR, p, st);

@@ -96,14 +96,32 @@ k_spconv_tc(const __grid_constant__ CUtensorMap tmB, const SptP p) {
         int pend[LA + 1]; int npend = 0;
 #pragma unroll
         for (int i = 0; i <= LA; ++i) pend[i] = 0;
+        // The tile's rulebook rows (128 x K ints, contiguous) are prefetched into REGISTERS one tile ahead: the loads fly under the
+        // current tile's gathers, so a tile starts without an exposed global-memory round trip (the first version re-read them at
+        // every tile start: ~2 us of bubble per tile, profiles/ncu_full_r2_summary.json: long_scoreboard-bound at 14 % occupancy)
+        int nxt[27];
+        auto fetch = [&](int tile_) {
+            const long long base = (long long)tile_ * SPT_M * p.K;
+            const int lim = min(SPT_M, Md - tile_ * SPT_M) * p.K;
+#pragma unroll
+            for (int q = 0; q < 27; ++q) {
+                const int i = tid + 128 * q;
+                nxt[q] = (q < p.K && i < lim) ? __ldg(p.nbr + base + i) : -1;
+            }
+        };
+        if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int row0 = tile * SPT_M;
             prod_bar();                               // every producer has issued the previous tile's copies (they read snbr)
             if (tid == 0) smask[0] = 0u;
-            for (int i = tid; i < SPT_M * p.K; i += 128) {
-                const int r = i / p.K, k = i - r * p.K;
-                snbr[r * KPAD + k] = (row0 + r < Md) ? __ldg(p.nbr + (size_t)row0 * p.K + i) : -1;
+#pragma unroll
+            for (int q = 0; q < 27; ++q) {
+                if (q < p.K) {
+                    const int i = tid + 128 * q;
+                    const int r = i / p.K, k = i - r * p.K;
+                    snbr[r * KPAD + k] = nxt[q];
+                }
             }
+            if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
             prod_bar();
             {   // active K-blocks of this tile = OR over its rows
                 unsigned m = 0;
