@@ -17,6 +17,11 @@ class HealAct(ctypes.Structure):
 
 _ap = ctypes.POINTER(HealAct)
 
+
+class HealCavHeads(ctypes.Structure):
+    """heal_cav_heads_t of include/heal_b200.h"""
+    _fields_ = [("cls", _ap), ("reg", _ap), ("dir", _ap), ("iou", _ap), ("anchors", _vp), ("transform4x4_host", ctypes.POINTER(ctypes.c_float))]
+
 # name -> (restype, argtypes); must list every symbol include/heal_b200.h declares
 SIGNATURES = {
     "heal_abi_version": (_i, []),
@@ -42,6 +47,8 @@ SIGNATURES = {
     "heal_postprocess_workspace": (_sz, [_i, _i, _i, _i]),
     "heal_box_decode_nms": (_i, [_ap, _ap, _ap, _vp, _i, _i, _i, _c.c_float, _c.c_float, _i, _vp, _i, _c.c_float, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "heal_box_decode_nms_multi": (_i, [ctypes.POINTER(HealCavHeads), _i, _i, _i, _i, _c.c_float, _c.c_float, _i, _i, _c.c_float, _i,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "heal_spconv_table_size": (_sz, [_i]),
     "heal_spconv_build_table": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "heal_spconv_subm_neighbors": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

@@ -23,7 +23,8 @@
 namespace {
 
 struct DecP {
-    ActV cls, reg, dir;            // (1,H,W,A) logits, (1,H,W,7A) deltas, (1,H,W,A*bins) or null -- fp32 channels-last
+    ActV cls, reg, dir, iou;       // (1,H,W,A) logits, (1,H,W,7A) deltas, (1,H,W,A*bins) or null, (1,H,W,A) IoU logits or null -- fp32 channels-last
+    int base;                      // first candidate slot of this cav (late fusion: the cavs' anchors are concatenated in cav order)
     const float* anchors;          // (H,W,A,7)
     int H, W, A, bins, hwl;
     float thr, dir_offset;
@@ -42,7 +43,8 @@ k_decode(DecP p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int a = i % p.A; const size_t pix = (size_t)(i / p.A);
-    p.vals[i] = i;
+    const int slot = p.base + i;
+    p.vals[slot] = slot;
     float key = -1.f;
     const float prob = 1.f / (1.f + expf(-ldf(p.cls, pix, a)));
     if (prob > p.thr) {
@@ -92,12 +94,17 @@ k_decode(DecP p) {
         if (keep) {
             atomicAdd(p.counters + 1, 1);
             key = prob;
-            float* o = p.cand + (size_t)i * 24;
+            if (p.iou.p) {     // voxel_postprocessor.py:343-347: score *= ((clamp(sigmoid(iou), 0, 1) + 1) / 2) ^ 4
+                float q = 1.f / (1.f + expf(-ldf(p.iou, pix, a)));
+                q = (fminf(fmaxf(q, 0.f), 1.f) + 1.f) * 0.5f;
+                key = prob * powf(q, 4.f);
+            }
+            float* o = p.cand + (size_t)slot * 24;
 #pragma unroll
             for (int k = 0; k < 24; ++k) o[k] = c[k];
         }
     }
-    p.keys[i] = key;
+    p.keys[slot] = key;
 }
 
 // top rows: [24 corner floats]; poly rows: 8 doubles (ccw x0 y0 .. x3 y3) + area
@@ -286,31 +293,39 @@ extern "C" size_t heal_postprocess_workspace(int H, int W, int anchors_per_cell,
     return layout(H * W * anchors_per_cell, top).total;
 }
 
-extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal_act_t* dir, const float* anchors,
-                                   int H, int W, int anchors_per_cell, float score_threshold, float dir_offset, int num_bins,
-                                   const float* transform4x4_host, int order_hwl, float nms_threshold, int top,
-                                   const float* range6_host, float* boxes_out, float* scores_out, int* count_out, int* stats_out,
-                                   void* workspace, size_t workspace_bytes, void* stream_) {
-    if (!cls || !cls->data || !reg || !reg->data || !anchors || !transform4x4_host || !boxes_out || !scores_out || !count_out || !workspace)
-        return HEAL_ERR_ARG;
-    if (cls->fmt != 0 || reg->fmt != 0 || (dir && dir->data && dir->fmt != 0)) return HEAL_ERR_UNSUPPORTED;
+extern "C" int heal_box_decode_nms_multi(const heal_cav_heads_t* cavs_host, int n_cav, int H, int W, int anchors_per_cell,
+                                         float score_threshold, float dir_offset, int num_bins, int order_hwl, float nms_threshold,
+                                         int top, const float* range6_host, float* boxes_out, float* scores_out, int* count_out,
+                                         int* stats_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!cavs_host || n_cav < 1 || n_cav > 16 || !boxes_out || !scores_out || !count_out || !workspace) return HEAL_ERR_ARG;
     if (H < 1 || W < 1 || anchors_per_cell < 1 || top < 1 || top > 1320 || num_bins < 1) return HEAL_ERR_ARG;   // mask must fit 227 KiB of smem
-    const int n = H * W * anchors_per_cell;
+    const int n1 = H * W * anchors_per_cell;
+    const long long nt = (long long)n1 * n_cav;
+    if (nt >= (1LL << 30)) return HEAL_ERR_UNSUPPORTED;
+    const int n = (int)nt;
     const WsLayout L = layout(n, top);
     if (workspace_bytes < L.total) return HEAL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
     uint8_t* ws = (uint8_t*)workspace;
     DecP p;
-    p.cls = to_view(cls); p.reg = to_view(reg);
-    if (dir && dir->data) p.dir = to_view(dir); else { p.dir = p.cls; p.dir.p = nullptr; }
-    p.anchors = anchors; p.H = H; p.W = W; p.A = anchors_per_cell; p.bins = num_bins; p.hwl = order_hwl ? 1 : 0;
+    p.H = H; p.W = W; p.A = anchors_per_cell; p.bins = num_bins; p.hwl = order_hwl ? 1 : 0;
     p.thr = score_threshold; p.dir_offset = dir_offset;
-    for (int k = 0; k < 12; ++k) p.T[k] = transform4x4_host[k];
     p.keys = (float*)(ws + L.keys_in); p.vals = (int*)(ws + L.vals_in); p.cand = (float*)(ws + L.cand);
     p.counters = (int*)(ws + L.counters);
     cudaMemsetAsync(p.counters, 0, 16, st);
     cudaMemsetAsync(ws + L.mask, 0, (size_t)top * L.words * 8, st);
-    k_decode<<<(n + 255) / 256, 256, 0, st>>>(p);
+    for (int c = 0; c < n_cav; ++c) {
+        const heal_cav_heads_t& h = cavs_host[c];
+        if (!h.cls || !h.cls->data || !h.reg || !h.reg->data || !h.anchors || !h.transform4x4_host) return HEAL_ERR_ARG;
+        if (h.cls->fmt != 0 || h.reg->fmt != 0 || (h.dir && h.dir->data && h.dir->fmt != 0) || (h.iou && h.iou->data && h.iou->fmt != 0))
+            return HEAL_ERR_UNSUPPORTED;
+        p.cls = to_view(h.cls); p.reg = to_view(h.reg);
+        if (h.dir && h.dir->data) p.dir = to_view(h.dir); else { p.dir = p.cls; p.dir.p = nullptr; }
+        if (h.iou && h.iou->data) p.iou = to_view(h.iou); else { p.iou = p.cls; p.iou.p = nullptr; }
+        p.anchors = h.anchors; p.base = c * n1;
+        for (int k = 0; k < 12; ++k) p.T[k] = h.transform4x4_host[k];
+        k_decode<<<(n1 + 255) / 256, 256, 0, st>>>(p);
+    }
     size_t cb = L.cub_bytes;
     if (cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cb, (const float*)p.keys, (float*)(ws + L.keys_out), (const int*)p.vals,
                                                   (int*)(ws + L.vals_out), n, 0, 32, st) != cudaSuccess) return HEAL_ERR_LAUNCH;
@@ -329,5 +344,16 @@ extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg,
     k_emit<<<top, 32, 0, st>>>((const int*)(ws + L.keep), count_out, (const float*)(ws + L.top_c), (const float*)(ws + L.top_s),
                                boxes_out, scores_out);
     if (stats_out) cudaMemcpyAsync(stats_out, p.counters, 8, cudaMemcpyDeviceToDevice, st);
-    return heal_check_launch(5);
+    return heal_check_launch(4 + n_cav);
+}
+
+extern "C" int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal_act_t* dir, const float* anchors,
+                                   int H, int W, int anchors_per_cell, float score_threshold, float dir_offset, int num_bins,
+                                   const float* transform4x4_host, int order_hwl, float nms_threshold, int top,
+                                   const float* range6_host, float* boxes_out, float* scores_out, int* count_out, int* stats_out,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
+    heal_cav_heads_t h;
+    h.cls = cls; h.reg = reg; h.dir = dir; h.iou = nullptr; h.anchors = anchors; h.transform4x4_host = transform4x4_host;
+    return heal_box_decode_nms_multi(&h, 1, H, W, anchors_per_cell, score_threshold, dir_offset, num_bins, order_hwl, nms_threshold, top,
+                                     range6_host, boxes_out, scores_out, count_out, stats_out, workspace, workspace_bytes, stream_);
 }

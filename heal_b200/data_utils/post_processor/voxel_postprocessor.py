@@ -52,12 +52,34 @@ class VoxelPostprocessor:
         raise NotImplementedError("heal_b200 covers the inference path; training targets stay in opencood")
 
     # -- voxel_postprocessor.py:245-405 ---------------------------------------------------------
+    def _decode_many(self, data_dict, output_dict):
+        """several cavs (late fusion) and / or iou_preds: heal_box_decode_nms_multi"""
+        cavs, dirs = [], []
+        for cav, out in output_dict.items():
+            cls = out.get('cls_preds', out.get('psm'))
+            reg = out.get('reg_preds', out.get('rm'))
+            if reg.dim() != 4:
+                raise NotImplementedError("anchor-free (CenterPoint) heads are not part of the GPU post-processor")
+            dirp = out.get('dir_preds', out.get('dm'))
+            dirs.append(dirp is not None)
+            cavs.append({"cls": cls, "reg": reg, "dir": dirp, "iou": out.get('iou_preds'),
+                         "anchors": self._device_anchors(data_dict[cav]['anchor_box'], cls.device),
+                         "transform": data_dict[cav]['transformation_matrix']})
+        A, H, W = cavs[0]["cls"].shape[1], cavs[0]["cls"].shape[2], cavs[0]["cls"].shape[3]
+        bkey = (H * len(cavs), W, A, str(cavs[0]["cls"].device))
+        if bkey not in self._buffers:
+            self._buffers[bkey] = ops.PostprocessBuffers(H * len(cavs), W, A, 1000, cavs[0]["cls"].device)
+        dargs = self.params.get('dir_args', {}) if any(dirs) else {}
+        return ops.box_decode_nms_multi(cavs, self.params['target_args']['score_threshold'], self.params['nms_thresh'],
+                                        dir_offset=dargs.get('dir_offset', 0.0), num_bins=dargs.get('num_bins', 2),
+                                        order=self.params['order'], gt_range=self.params['gt_range'], top=1000, buffers=self._buffers[bkey])
+
     def _decode_one(self, cav_content, out):
         cls = out.get('cls_preds', out.get('psm'))
         reg = out.get('reg_preds', out.get('rm'))
         dirp = out.get('dir_preds', out.get('dm'))
         if 'iou_preds' in out:
-            raise NotImplementedError("iou_preds rescoring is not part of the GPU post-processor")
+            raise NotImplementedError("use _decode_many for iou_preds rescoring")
         if reg.dim() != 4:
             raise NotImplementedError("anchor-free (CenterPoint) heads are not part of the GPU post-processor")
         dev = cls.device
@@ -89,13 +111,13 @@ class VoxelPostprocessor:
 
     def post_process(self, data_dict, output_dict):
         """Returns (pred_box3d_tensor (K,8,3), scores (K,)) on the device, or (None, None).  One cav (early / intermediate fusion:
-        the ego); late fusion's cross-cav NMS stays with the reference."""
+        the ego) or several (late fusion: every cav's boxes projected to ego, one NMS over all of them), with optional iou_preds."""
         cavs = list(output_dict.keys())
-        if len(cavs) != 1:
-            raise NotImplementedError("late fusion (NMS across several cavs' boxes) is not part of the GPU post-processor")
-        cav = cavs[0]
-        assert cav in data_dict
-        buf = self._decode_one(data_dict[cav], output_dict[cav])
+        assert all(c in data_dict for c in cavs)
+        if len(cavs) != 1 or 'iou_preds' in output_dict[cavs[0]]:
+            buf = self._decode_many(data_dict, output_dict)          # late fusion: NMS across all cavs' boxes; iou rescoring
+        else:
+            buf = self._decode_one(data_dict[cavs[0]], output_dict[cavs[0]])
         # the only host sync of the call: box count + candidate count in ONE device-to-host copy (the reference-shaped return
         # needs the box count; the 4x4 transform is host metadata in the reference's collate and is read before the launch)
         k, above = torch.cat([buf.count, buf.stats[:1]]).tolist()
@@ -108,8 +130,8 @@ def make_reference_subclass(ref_cls):
     """Build the class the registry hook installs: a SUBCLASS of the reference's own VoxelPostprocessor (so the datasets keep
     generate_label / generate_gt_bbx / generate_object_center* / collate_batch, which they call on the inference path too:
     intermediate_heter_fusion_dataset.py:179,458,537,666,781; opv2v_basedataset.py:435) whose `post_process` runs on the GPU
-    when it can (one cav, anchor-based heads on a CUDA device, no iou_preds) and defers to the reference implementation otherwise
-    (late fusion's cross-cav NMS, iou rescoring, CPU tensors)."""
+    when it can (anchor-based heads of equal geometry on a CUDA device: one cav, or several = late fusion, with or without
+    iou_preds) and defers to the reference implementation otherwise (CPU tensors, anchor-free heads)."""
     gpu = VoxelPostprocessor
 
     class GpuVoxelPostprocessor(ref_cls):
@@ -119,12 +141,18 @@ def make_reference_subclass(ref_cls):
 
         @staticmethod
         def _gpu_eligible(output_dict):
-            if len(output_dict) != 1:
+            if not (1 <= len(output_dict) <= 16):
                 return False
-            out = next(iter(output_dict.values()))
-            cls = out.get('cls_preds', out.get('psm'))
-            reg = out.get('reg_preds', out.get('rm'))
-            return ('iou_preds' not in out and torch.is_tensor(cls) and cls.is_cuda and torch.is_tensor(reg) and reg.dim() == 4)
+            shape = None
+            for out in output_dict.values():
+                cls = out.get('cls_preds', out.get('psm'))
+                reg = out.get('reg_preds', out.get('rm'))
+                if not (torch.is_tensor(cls) and cls.is_cuda and torch.is_tensor(reg) and reg.dim() == 4):
+                    return False
+                if shape is not None and tuple(cls.shape) != shape:
+                    return False                      # cavs with different head geometry: reference path
+                shape = tuple(cls.shape)
+            return True
 
         def post_process(self, data_dict, output_dict):
             if self._gpu_eligible(output_dict):

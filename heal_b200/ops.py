@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import lib, check, HealAct
+from ._lib import lib, check, HealAct, HealCavHeads
 
 _vp = ctypes.c_void_p
 FMT = {"f32": 0, "bf16": 1, "split": 2}
@@ -1066,3 +1066,48 @@ for _name in ("dwconv_layernorm", "maxpool3x3s2", "convert", "voxelize", "mean_v
               "lss_cell_index", "lss_pool", "lss_pool_sorted", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
               "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
     globals()[_name] = _guard(globals()[_name])
+
+
+def box_decode_nms_multi(cavs, score_threshold: float, nms_threshold: float, dir_offset: float = 0.0, num_bins: int = 2,
+                         order: str = "hwl", gt_range=None, top: int = 1000, buffers: Optional[PostprocessBuffers] = None) -> PostprocessBuffers:
+    """VoxelPostprocessor.post_process for SEVERAL cavs (late fusion) and / or `iou_preds` rescoring on the GPU, no host sync.
+    cavs: list of dicts {cls, reg, dir | None, iou | None, anchors (H,W,A,7) fp32 device, transform (4x4 host values)}; all cavs share
+    H, W, A.  Candidates are concatenated in list order, then filtered, sorted and NMS-ed together (voxel_postprocessor.py:269-397)."""
+    n = len(cavs)
+    assert n >= 1
+    keep = []           # keep the views / arrays alive until the call returns
+    arr = (HealCavHeads * n)()
+    H = W = A = None
+    for i, c in enumerate(cavs):
+        cl, rg = _head_act(c["cls"]), _head_act(c["reg"])
+        dr = _head_act(c["dir"]) if c.get("dir") is not None else None
+        io = _head_act(c["iou"]) if c.get("iou") is not None else None
+        if H is None:
+            H, W, A = cl.H, cl.W, cl.C
+        assert (cl.H, cl.W, cl.C) == (H, W, A) and cl.N == 1 and rg.C == 7 * A
+        an = c["anchors"]
+        _need_cuda(an)
+        assert an.dtype == torch.float32 and an.is_contiguous() and an.numel() == H * W * A * 7
+        views = [cl.view(), rg.view(), dr.view() if dr is not None else None, io.view() if io is not None else None]
+        T = _host_f32(np.asarray(torch.as_tensor(c["transform"]).detach().cpu().numpy(), dtype=np.float64).reshape(16))
+        keep.append((cl, rg, dr, io, views, T, an))
+        arr[i].cls, arr[i].reg = ctypes.pointer(views[0]), ctypes.pointer(views[1])
+        arr[i].dir = ctypes.pointer(views[2]) if views[2] is not None else None
+        arr[i].iou = ctypes.pointer(views[3]) if views[3] is not None else None
+        arr[i].anchors = an.data_ptr()
+        arr[i].transform4x4_host = ctypes.cast(T, ctypes.POINTER(ctypes.c_float))
+    dev = cavs[0]["anchors"].device
+    if buffers is None:
+        buffers = PostprocessBuffers(H * n, W, A, top, dev)
+    assert (buffers.H, buffers.W, buffers.A, buffers.top) == (H * n, W, A, top)
+    rng = _host_f32(gt_range) if gt_range is not None else None
+    with _Prof("box_decode_nms", 0):
+        rc = lib.heal_box_decode_nms_multi(arr, n, H, W, A, float(score_threshold), float(np.float32(dir_offset)), int(num_bins),
+                                           1 if order == "hwl" else 0, float(nms_threshold), int(top), rng,
+                                           _p(buffers.boxes), _p(buffers.scores), _p(buffers.count), _p(buffers.stats),
+                                           _p(buffers.workspace), buffers.workspace.numel(), _stream())
+    check(rc, "heal_box_decode_nms_multi")
+    return buffers
+
+
+box_decode_nms_multi = _guard(box_decode_nms_multi)

@@ -268,6 +268,21 @@ int heal_box_decode_nms(const heal_act_t* cls, const heal_act_t* reg, const heal
                         const float* range6_host, float* boxes_out, float* scores_out, int* count_out, int* stats_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Late fusion / IoU-aware variant (voxel_postprocessor.py:269-376 with several cavs and `iou_preds`): every cav's heads are decoded
+ * with ITS transform (cav -> ego) and anchors, the candidates are concatenated in cav order, then ONE filter + sort + rotated NMS
+ * + range mask.  `iou` (optional, (1,H,W,A) logits): score *= ((sigmoid(iou) + 1) / 2)^4 after the threshold test (:343-347).
+ * cavs_host: HOST array of n_cav descriptors (all maps H x W x anchors_per_cell); workspace >=
+ * heal_postprocess_workspace(H * n_cav, W, anchors_per_cell, top). */
+typedef struct {
+    const heal_act_t* cls; const heal_act_t* reg; const heal_act_t* dir; const heal_act_t* iou;   /* dir / iou may be NULL */
+    const float* anchors;                 /* device (H,W,A,7) */
+    const float* transform4x4_host;       /* host, row-major 4x4 */
+} heal_cav_heads_t;
+int heal_box_decode_nms_multi(const heal_cav_heads_t* cavs_host, int n_cav, int H, int W, int anchors_per_cell,
+                              float score_threshold, float dir_offset, int num_bins, int order_hwl, float nms_threshold,
+                              int top, const float* range6_host, float* boxes_out, float* scores_out, int* count_out,
+                              int* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- format conversion between fp32 and (split-)bf16 channels-last buffers ------------------- */
 int heal_act_convert(const heal_act_t* src, const heal_act_t* dst, size_t num_pixels, int channels, void* stream);
 

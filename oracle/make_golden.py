@@ -262,7 +262,26 @@ def make_postprocess_golden():
             boxes, scores = pp.post_process(data, out)
         cases[name] = {"cls": cls, "reg": reg, "dir": dirp, "T": T, "boxes": boxes, "scores": scores}
         print("postprocess", name, "candidates", int((torch.sigmoid(cls) > 0.2).sum()), "-> kept", 0 if boxes is None else boxes.shape[0])
-    torch.save({"params": params, "anchors": anchors, "cases": cases}, os.path.join(OUT, "postprocess.pt"))
+    # late fusion (two cavs, each with its own cav->ego transform; one NMS over both box sets) and iou_preds rescoring
+    multi = {}
+    T2 = torch.tensor([[np.cos(-0.4), -np.sin(-0.4), 0, -3.0], [np.sin(-0.4), np.cos(-0.4), 0, 2.5], [0, 0, 1, -0.05], [0, 0, 0, 1]],
+                      dtype=torch.float32)
+    heads = [postprocess_inputs(params, 5, -4.0), postprocess_inputs(params, 6, -4.0)]
+    data = {"ego": {"transformation_matrix": heads[0][3], "anchor_box": anchors}, "cav1": {"transformation_matrix": T2, "anchor_box": anchors}}
+    out = {k: {"cls_preds": h[0].clone(), "reg_preds": h[1].clone(), "dir_preds": h[2].clone()} for k, h in zip(("ego", "cav1"), heads)}
+    with torch.no_grad():
+        boxes, scores = pp.post_process(data, out)
+    multi["late2"] = {"cavs": [{"cls": h[0], "reg": h[1], "dir": h[2], "T": t} for h, t in zip(heads, (heads[0][3], T2))],
+                      "boxes": boxes, "scores": scores}
+    print("postprocess late2 -> kept", boxes.shape[0])
+    cls, reg, dirp, T = postprocess_inputs(params, 7, -3.5)
+    iou = torch.randn(cls.shape, generator=torch.Generator().manual_seed(17))
+    with torch.no_grad():
+        boxes, scores = pp.post_process({"ego": {"transformation_matrix": T, "anchor_box": anchors}},
+                                        {"ego": {"cls_preds": cls.clone(), "reg_preds": reg.clone(), "dir_preds": dirp.clone(), "iou_preds": iou.clone()}})
+    multi["iou"] = {"cavs": [{"cls": cls, "reg": reg, "dir": dirp, "iou": iou, "T": T}], "boxes": boxes, "scores": scores}
+    print("postprocess iou -> kept", boxes.shape[0])
+    torch.save({"params": params, "anchors": anchors, "cases": cases, "multi": multi}, os.path.join(OUT, "postprocess.pt"))
 
 
 if __name__ == "__main__":

@@ -76,3 +76,23 @@ def test_model_heads_feed_the_postprocessor_without_copies(gold):
     b1, s1 = pp.post_process({"ego": {"transformation_matrix": c["T"], "anchor_box": gold["anchors"]}},
                              {"ego": {"cls_preds": cl(c["cls"]), "reg_preds": cl(c["reg"]), "dir_preds": cl(c["dir"])}})
     assert torch.equal(b0, b1) and torch.equal(s0, s1)
+
+
+@pytest.mark.parametrize("case", ["late2", "iou"])
+def test_late_fusion_and_iou_rescoring_vs_reference_golden(gold, case):
+    """heal_box_decode_nms_multi: two cavs with their own cav->ego transforms (late fusion, one NMS over both box sets) and
+    `iou_preds` rescoring, against the UNMODIFIED reference VoxelPostprocessor.post_process (tests/golden/postprocess.pt `multi`)."""
+    from heal_b200.data_utils.post_processor import build_postprocessor
+    c = gold["multi"][case]
+    pp = build_postprocessor(copy.deepcopy(gold["params"]), train=False)
+    names = ["ego"] + [f"cav{i}" for i in range(1, len(c["cavs"]))]
+    data = {n: {"transformation_matrix": cav["T"], "anchor_box": gold["anchors"]} for n, cav in zip(names, c["cavs"])}
+    out = {}
+    for n, cav in zip(names, c["cavs"]):
+        out[n] = {"cls_preds": cav["cls"].cuda(), "reg_preds": cav["reg"].cuda(), "dir_preds": cav["dir"].cuda()}
+        if "iou" in cav:
+            out[n]["iou_preds"] = cav["iou"].cuda()
+    boxes, scores = pp.post_process(data, out)
+    assert boxes.shape == c["boxes"].shape, (boxes.shape, c["boxes"].shape)
+    torch.testing.assert_close(scores.cpu(), c["scores"], rtol=0, atol=1e-6)
+    torch.testing.assert_close(boxes.cpu(), c["boxes"], rtol=0, atol=1e-4)

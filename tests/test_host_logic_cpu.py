@@ -83,5 +83,6 @@ def test_postprocessor_anchor_box_equals_reference_golden(golden_dir):
     import pytest
     with pytest.raises(NotImplementedError):
         pp.generate_label()
-    with pytest.raises(NotImplementedError):      # late fusion: several cavs
-        pp.post_process({"a": {}, "b": {}}, {"a": {}, "b": {}})
+    with pytest.raises(NotImplementedError):      # anchor-free (CenterPoint) heads are outside the GPU post-processor
+        pp.post_process({"a": {"anchor_box": g["anchors"]}},
+                        {"a": {"cls_preds": torch.zeros(1, 2, 4, 4), "reg_preds": torch.zeros(1, 32, 7), "iou_preds": torch.zeros(1, 2, 4, 4)}})
