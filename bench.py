@@ -773,6 +773,10 @@ def run_gpu(opt):
                         "tensor_pipe_tflops": ach * mma_per_flop if ach else None,
                         "tensor_pipe_frac": ach * mma_per_flop / peak_tf if ach else None,
                         "ms_per_frame": ms, "share_of_step": ms / (total_ms / opt.steps),
+                        "achieved_over_whole_graph_step": (gf / 1e3) / (total_ms / opt.steps / 1e3),
+                        "share_note": "the per-family times come from an EAGER instrumented pass (events around every C-ABI call) and are upper "
+                                      "bounds of the in-graph times: their sum can exceed the graph step; `achieved_over_whole_graph_step` = conv "
+                                      "FLOPs / the whole captured step (a lower bound of the kernel's own rate)",
                         "hbm": {"achieved": (mb / 1e3) / (ms / 1e3) if ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": ((mb / 1e3) / (ms / 1e3)) / hbm_peak if ms > 0 else None,
                                 "note": "ALGORITHMIC conv bytes (each layer's input + weights + output + residual, once) / live launch time"},

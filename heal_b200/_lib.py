@@ -29,6 +29,8 @@ SIGNATURES = {
     "heal_launch_count": (_c.c_longlong, []),
     "heal_voxelize_workspace": (_sz, [_i, _i, _i]),
     "heal_voxelize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "heal_mask_points_workspace": (_sz, [_i]),
+    "heal_mask_points": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "heal_mean_vfe": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "heal_pillar_vfe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _ap, _vp]),
     "heal_pillar_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ap, _vp]),

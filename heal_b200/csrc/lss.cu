@@ -188,24 +188,30 @@ k_lss_pool_chunks(SortedP p, const unsigned* __restrict__ keys, const int* __res
         s_edge[1] = (nx >= total_cells) ? LSS_NONE : nx;
     }
     __syncthreads();
+    // number of valid points in this chunk (valid keys sort before the invalid tail)
+    const int nvalid = __syncthreads_count(tid < LSS_CH && s_key[tid < LSS_CH ? tid : 0] != LSS_NONE);
     if (ch >= p.C) return;
     unsigned cur = s_key[0];
-    if (cur == LSS_NONE) return;                       // the whole chunk lies in the invalid tail
+    if (nvalid == 0) return;                           // the whole chunk lies in the invalid tail
     bool started_here = (s_edge[0] != cur);
     float acc = 0.f;
     float* mypart = part + (size_t)blockIdx.x * 2 * p.C;
-    int t = 0;
-#pragma unroll 4
-    for (; t < LSS_CH; ++t) {
+    const float* fch = p.feat + (long long)ch * p.f_c;
+    auto step = [&](int t, float f) {
         const unsigned k = s_key[t];
-        if (k == LSS_NONE) break;
         if (k != cur) {                                // the cell `cur` ended inside this chunk
             if (started_here) act_store1(p.out, (size_t)cur, ch, acc);
             else { mypart[ch] = acc; if (ch == 0) pkey[2 * blockIdx.x] = cur; }
             acc = 0.f; cur = k; started_here = true;
         }
-        acc = fmaf(s_pr[t], __ldg(p.feat + s_fo[t] + (long long)ch * p.f_c), acc);
+        acc = fmaf(s_pr[t], f, acc);
+    };
+    int t = 0;
+    for (; t + 4 <= nvalid; t += 4) {                  // four independent feature loads in flight, then the ordered accumulation
+        const float f0 = __ldg(fch + s_fo[t]), f1 = __ldg(fch + s_fo[t + 1]), f2 = __ldg(fch + s_fo[t + 2]), f3 = __ldg(fch + s_fo[t + 3]);
+        step(t, f0); step(t + 1, f1); step(t + 2, f2); step(t + 3, f3);
     }
+    for (; t < nvalid; ++t) step(t, __ldg(fch + s_fo[t]));
     const unsigned nextk = (t < LSS_CH) ? LSS_NONE : s_edge[1];
     const bool ended_here = (nextk != cur);
     if (started_here && ended_here) act_store1(p.out, (size_t)cur, ch, acc);

@@ -48,7 +48,7 @@ class PointPillar(nn.Module):
             if batch_size is None:
                 batch_size = int(vc[:, 0].max().item()) + 1     # host sync, as the reference (scatter.py:45)
         else:
-            pts, offs = inp['points'], inp['agent_offsets']
+            pts, offs = ops.raw_points_of(inp, self.lidar_range)
             vf, vc, vn, nvox_dev = ops.voxelize(pts, offs, self.lidar_range, self.voxel_size,
                                                 int(inp.get('max_points_per_voxel', self.voxelize_args['max_points_per_voxel'])),
                                                 int(inp.get('max_voxels', self.voxelize_args['max_voxels'])))
@@ -308,7 +308,8 @@ class SECOND(nn.Module):
             if batch_size is None:
                 batch_size = int(vc[:, 0].max().item()) + 1          # host sync, as the reference (heter_encoders.py:70)
         else:
-            vf, vc, vn, nvox = ops.voxelize(inp['points'], inp['agent_offsets'], self.lidar_range, self.voxel_size,
+            pts, offs = ops.raw_points_of(inp, self.lidar_range)
+            vf, vc, vn, nvox = ops.voxelize(pts, offs, self.lidar_range, self.voxel_size,
                                             int(inp.get('max_points_per_voxel', self.voxelize_args['max_points_per_voxel'])),
                                             int(inp.get('max_voxels', self.voxelize_args['max_voxels'])))
             rows_dev = nvox[0:1]

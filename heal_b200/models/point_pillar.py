@@ -54,7 +54,8 @@ class PointPillar(nn.Module):
         else:
             # raw points (`points`, `agent_offsets`): GPU voxelisation, no host sync (graph-capturable frame)
             va = self.voxelize_args
-            vf, vc, vn, nvox_dev = ops.voxelize(inp['points'], inp['agent_offsets'], self.lidar_range, self.voxel_size,
+            pts, offs = ops.raw_points_of(inp, self.lidar_range)
+            vf, vc, vn, nvox_dev = ops.voxelize(pts, offs, self.lidar_range, self.voxel_size,
                                                 int(inp.get('max_points_per_voxel', va['max_points_per_voxel'])),
                                                 int(inp.get('max_voxels', va['max_voxels'])))
             batch_size = inp['agent_offsets'].numel() - 1

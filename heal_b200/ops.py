@@ -238,6 +238,34 @@ def voxelize(points: torch.Tensor, agent_offsets: torch.Tensor, lidar_range, vox
     return voxels, coords, npts, nvox
 
 
+def mask_points(points: torch.Tensor, agent_offsets: torch.Tensor, lidar_range, remove_ego: bool = True,
+                perm: Optional[torch.Tensor] = None):
+    """shuffle_points (host-drawn `perm`, optional) -> mask_ego_points -> mask_points_by_range on the GPU (pcd_utils.py:41-95), a
+    stable compaction per agent.  Returns (points_out (P,4) f32 [rows >= offsets_out[-1] undefined], offsets_out (A+1) i32 device)."""
+    _need_cuda(points, agent_offsets)
+    assert points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 4 and points.is_contiguous()
+    assert agent_offsets.dtype == torch.int32
+    P, A = points.shape[0], agent_offsets.numel() - 1
+    out = torch.empty_like(points)
+    offs_out = torch.empty_like(agent_offsets)
+    ws = _workspace(points.device, lib.heal_mask_points_workspace(P))
+    pm = perm.to(torch.int32).contiguous() if perm is not None else None
+    with _Prof("mask_points", 0, 32.0 * P):
+        rc = lib.heal_mask_points(_p(points), _p(pm), _p(agent_offsets), A, P, _host_f32(lidar_range), 1 if remove_ego else 0,
+                                  _p(out), _p(offs_out), _p(ws), ws.numel(), _stream())
+    check(rc, "heal_mask_points")
+    return out, offs_out
+
+
+def raw_points_of(inp: dict, lidar_range):
+    """(points, agent_offsets) of a raw-points `inputs_<m>` dict.  With `filter_points` set (GpuVoxelPreprocessor, `filter_on_gpu`),
+    the clouds are still unfiltered and the reference's host filters run here first (mask_points); otherwise as given."""
+    pts, offs = inp['points'], inp['agent_offsets']
+    if inp.get('filter_points'):
+        pts, offs = mask_points(pts, offs, lidar_range, bool(inp.get('remove_ego', True)), inp.get('shuffle_perm'))
+    return pts, offs
+
+
 def trim_voxels(voxels, coords, npts, nvox):
     m = int(nvox[0].item())
     return {"voxel_features": voxels[:m], "voxel_coords": coords[:m], "voxel_num_points": npts[:m]}
@@ -1062,7 +1090,7 @@ def _guard(fn):
     return wrapped
 
 
-for _name in ("dwconv_layernorm", "maxpool3x3s2", "convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
+for _name in ("mask_points", "dwconv_layernorm", "maxpool3x3s2", "convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
               "lss_cell_index", "lss_pool", "lss_pool_sorted", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
               "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
     globals()[_name] = _guard(globals()[_name])

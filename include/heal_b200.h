@@ -309,6 +309,17 @@ int heal_maxpool3x3s2(const heal_act_t* in, int N, int H, int W, int C, int dept
 int heal_p2p_push(const void* src_local, void* const* peer_dst_host, int world, int self, size_t bytes, void* stream);
 int heal_p2p_signal_wait(void* const* peer_flags_host, int world, int self, unsigned* seq_dev, void* stream);
 
+/* ---- on-GPU input path: the reference's host-side point filters before voxelisation ----------------
+ * shuffle_points / mask_ego_points / mask_points_by_range (opencood/utils/pcd_utils.py:41-95, applied in this order by
+ * intermediate_heter_fusion_dataset.py:141-173) as one stable compaction per agent: points_out = mask(points[perm]).
+ *   points (P,4) f32, agents concatenated; perm (P) i32 GLOBAL source index per slot (the host-drawn shuffle) or NULL;
+ *   agent_offsets (A+1) i32 device (live count = offsets[A] <= P); range6_host = [xmin,ymin,zmin,xmax,ymax,zmax] (strict);
+ *   remove_ego != 0 drops the ego-vehicle box.  points_out (P,4); agent_offsets_out (A+1) i32 device. */
+size_t heal_mask_points_workspace(int num_points);
+int heal_mask_points(const float* points, const int* perm, const int* agent_offsets, int num_agents, int num_points,
+                     const float* range6_host, int remove_ego, float* points_out, int* agent_offsets_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,31 @@ def test_c1_full_size_vs_unmodified_reference():
     _check(out, ref, 1e-3, "C1-full/tc32")
 
 
+def test_c1_gpu_point_filters_equal_host_filters():
+    """The on-GPU input path (filter_on_gpu): an UNFILTERED cloud + the host-drawn shuffle permutation through heal_mask_points ->
+    voxeliser -> model gives bit-identical predictions to the reference's host filters (oracle/pcd.py) feeding the same model."""
+    from oracle import pcd
+    from heal_b200 import engine
+    from heal_b200.models.point_pillar import PointPillar
+    engine.set_precision("tc32")
+    rng = np.random.default_rng(78)
+    cloud = synth.lidar_cloud(rng, rings=32, azimuth=1000)
+    cloud = np.concatenate([cloud, rng.uniform(-3, 3, size=(500, 4)).astype(np.float32),          # ego-box hits
+                            rng.uniform(-130, 130, size=(500, 4)).astype(np.float32)])             # out-of-range points
+    perm = rng.permutation(cloud.shape[0]).astype(np.int32)
+    host = pcd.filter_cloud(cloud, wcfg.RANGE, perm)
+    assert 0 < host.shape[0] < cloud.shape[0]
+    m = PointPillar(wcfg.c1_args()).eval()
+    m.load_state_dict(procedural.make_state_dict(procedural.shapes_of(m)), strict=True)
+    m = m.cuda()
+    with torch.no_grad():
+        a = m({"processed_lidar": {"points": torch.from_numpy(host).cuda(), "agent_offsets": torch.tensor([0, host.shape[0]], dtype=torch.int32).cuda()}})
+        b = m({"processed_lidar": {"points": torch.from_numpy(cloud).cuda(), "agent_offsets": torch.tensor([0, cloud.shape[0]], dtype=torch.int32).cuda(),
+                                   "filter_points": True, "remove_ego": True, "shuffle_perm": torch.from_numpy(perm).cuda()}})
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_c3_full_size_second_attfusion_vs_oracle():
     """configs[2]: SECOND (0.1 m voxels, 2048x2048x40 grid, ~300k voxels) + BaseBEVBackbone + per-agent shrinker + AttFusion, 5 agents."""
     from oracle import nets, sparse_conv as sc_, voxelizer

@@ -280,3 +280,39 @@ def test_sparse_stem_equals_dense_canvas_path_and_oracle(prec):
         engine.STEM_TC = old_tc
         ops.STEM_GATHER_TC = old_gather
         engine.set_precision(old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_perm,remove_ego", [(False, True), (True, True), (True, False)])
+def test_mask_points_bit_exact(use_perm, remove_ego):
+    """heal_mask_points == shuffle -> mask_ego_points -> mask_points_by_range (oracle/pcd.py, pinned to pcd_utils.py:41-95), per agent,
+    order included; then the voxeliser on the filtered cloud equals the oracle voxeliser on the oracle-filtered cloud."""
+    from heal_b200 import ops
+    from oracle import pcd
+    rng = np.random.default_rng(17)
+    clouds = []
+    for n in (30000, 1, 0, 12345):
+        p = rng.uniform(-120, 120, size=(n, 4)).astype(np.float32)
+        if n:
+            p[:, 2] = rng.uniform(-4, 2, size=n)
+            p[: n // 10, :2] = rng.uniform(-3, 3, size=(n // 10, 2))
+        clouds.append(p)
+    clouds[0][:4] = [[-1.95, 1.1, 0, 1], [102.4, 0, 0, 1], [5, 5, -3, 1], [2.95, -1.1, 0.5, 1]]
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    pts = np.concatenate(clouds)
+    perms = [rng.permutation(c.shape[0]) for c in clouds] if use_perm else [None] * len(clouds)
+    gperm = np.concatenate([pm + o for pm, o in zip(perms, offs[:-1])]).astype(np.int32) if use_perm else None
+    ref = [pcd.filter_cloud(c, PP_RANGE, pm, remove_ego) for c, pm in zip(clouds, perms)]
+    ref_offs = np.concatenate([[0], np.cumsum([r.shape[0] for r in ref])]).astype(np.int32)
+    # capacity larger than the live count: the tail rows must be ignored
+    cap = np.concatenate([pts, np.full((100, 4), 7.0, np.float32)])
+    out, o2 = ops.mask_points(_cuda(cap).contiguous(), _cuda(offs), PP_RANGE, remove_ego,
+                              _cuda(gperm) if use_perm else None)
+    assert np.array_equal(o2.cpu().numpy(), ref_offs)
+    assert np.array_equal(out[: ref_offs[-1]].cpu().numpy(), np.concatenate(ref))
+    v, c, n, nv = ops.voxelize(out, o2, PP_RANGE, PP_VOXEL, 32, 70000)
+    per_agent = [voxelizer.points_to_voxel_c(r, PP_VOXEL, PP_RANGE, 32, 70000) for r in ref]
+    col = voxelizer.collate(per_agent)
+    got = ops.trim_voxels(v, c, n, nv)
+    assert np.array_equal(got["voxel_coords"].cpu().numpy(), col["voxel_coords"])
+    assert np.array_equal(got["voxel_features"].cpu().numpy().view(np.uint32), col["voxel_features"].view(np.uint32))

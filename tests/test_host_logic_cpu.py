@@ -21,6 +21,17 @@ def test_gpu_voxel_preprocessor_contract():
     assert out["points"].shape == (17, 4) and out["agent_offsets"].tolist() == [0, 10, 17]
     out2 = pp.collate_batch({"points": [a["points"], b["points"]]})
     assert torch.equal(out2["points"], out["points"])
+    assert "filter_points" not in out
+    # filter_on_gpu: the shuffle permutation is drawn from numpy's global RNG exactly where shuffle_points would draw it
+    cfg["args"]["filter_on_gpu"] = True
+    pp = build_preprocessor(cfg, train=False)
+    np.random.seed(11)
+    a2, b2 = pp.preprocess(a["points"]), pp.preprocess(b["points"])
+    np.random.seed(11)
+    pa, pb = np.random.permutation(10), np.random.permutation(7)
+    out3 = pp.collate_batch([a2, b2])
+    assert out3["filter_points"] is True and out3["remove_ego"] is True
+    assert out3["shuffle_perm"].tolist() == list(pa) + [int(x) + 10 for x in pb]
 
 
 def test_state_dict_keys_match_reference(golden_dir):
