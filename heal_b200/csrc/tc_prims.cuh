@@ -1,4 +1,4 @@
-// tcgen05 / TMA / mbarrier primitives shared by the tensor-core kernels (conv2d_tc.cu, spconv_tc.cu, bottleneck_tc.cu).
+// tcgen05 / TMA / mbarrier primitives shared by the tensor-core kernels (conv2d_tc.cu, conv3x3_ring.cu, spconv_tc.cu).
 // Inline PTX for sm_100a; every helper is a thin wrapper around ONE instruction (or a bounded wait loop).
 #pragma once
 #include <cuda.h>
