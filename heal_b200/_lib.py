@@ -64,6 +64,7 @@ SIGNATURES = {
     "heal_sparse_to_bev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "heal_p2p_push": (_i, [_vp, _vp, _i, _i, _sz, _vp]),
     "heal_p2p_signal_wait": (_i, [_vp, _i, _i, _vp, _vp]),
+    "heal_lss_camera_matrices": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "heal_lss_cell_index": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "heal_lss_pool_sorted_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "heal_lss_pool_sorted": (_i, [_vp, _c.c_longlong, _c.c_longlong, _c.c_longlong, _vp, _c.c_longlong, _c.c_longlong, _c.c_longlong,

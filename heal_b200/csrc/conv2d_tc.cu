@@ -30,6 +30,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include "conv_ring.cuh"
 #include "../../include/heal_b200.h"
 
 namespace {
@@ -555,11 +556,11 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // HEAL_TC_* measurement hooks (profiles/tc_experiment.py), read once per process instead of six getenv calls per launch.
 struct TcEnv {
-    int dbg, pdl, halo, bo, tma_store, res_tma;
+    int dbg, pdl, halo, bo, tma_store, res_tma, ring;
     TcEnv() {
         auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
         dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 0); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
-        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1);
+        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1);
     }
 };
 const TcEnv& tc_env() { static const TcEnv e; return e; }
@@ -753,6 +754,15 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
     if (p.halo && p.bdiag) p.res_tma = 0;      // <64,4,1>: register prefetch
     cudaStream_t st = (cudaStream_t)stream_;
     const int kblocks = (blockdiag ? 1 : p.kc_blocks) * taps;
+    // grouped 3x3 on maps at least 128 pixels wide: the row-ring kernel (conv3x3_ring.cu) reads every input row and the weights
+    // once per CTA instead of three times / once per tile; it shares the three tensor maps built above
+    if (env.ring && p.halo && p.bdiag && p.tma_out && !res_split && !res_f32 && (Wo % 128) == 0 && relu != 2 && Cin == Cout &&
+        coutp == Cout && !p.dbg) {
+        RingP rp;
+        rp.N = N; rp.H = Ho; rp.W = Wo; rp.C = Cout; rp.planes = planes; rp.wplanes = w_planes; rp.relu = relu; rp.bias = bias;
+        rp.segs = 1; rp.seg_rows = Ho;
+        return heal_conv3x3_ring_launch(tmA, tmB, tmO, rp, st);
+    }
     if (relu == 2) {        // GELU: 1x1 / 3x3 convs with >= 128 output channels and no residual (ConvNeXt pwconv1: dim -> 4 dim)
         if (block_n != 128 || res_split || res_f32) return HEAL_ERR_UNSUPPORTED;
         if (!p.tma_out) return launch_tc<128, 3, 0, true>(tmA, tmB, tmO, tmR, p, st);

@@ -298,6 +298,47 @@ extern "C" int heal_lss_pool_sorted(const float* depth_logits, long long l_img, 
     return heal_check_launch(6);
 }
 
+// Per-camera 3x3 algebra of get_geometry (lss_submodule / heter_encoders.py:135,142): post_inv = inverse(post_rots),
+// combine = rots @ inverse(intrins).  torch.inverse is not capturable in a CUDA graph (cuSOLVER/cuBLAS pointer-array setup), so the
+// two inverses are closed-form adjugates evaluated in fp64 and rounded to fp32 (within 1 ulp of the exact inverse; the reference's
+// fp32 LU differs from it by a few ulp, which only matters for frustum points that sit on a cell boundary).
+__device__ __forceinline__ void inv3x3_f64(const float* m, double* o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    const double r = 1.0 / det;
+    o[0] = A * r; o[1] = -(b * i - c * h) * r; o[2] = (b * f - c * e) * r;
+    o[3] = B * r; o[4] = (a * i - c * g) * r;  o[5] = -(a * f - c * d) * r;
+    o[6] = C * r; o[7] = -(a * h - b * g) * r; o[8] = (a * e - b * d) * r;
+}
+
+__global__ void k_lss_camera_matrices(const float* __restrict__ rots, const float* __restrict__ intrins, const float* __restrict__ post_rots,
+                                      int n, float* __restrict__ post_inv, float* __restrict__ combine) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double pi[9], ii[9];
+    inv3x3_f64(post_rots + 9 * c, pi);
+    inv3x3_f64(intrins + 9 * c, ii);
+    float iif[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { post_inv[9 * c + j] = (float)pi[j]; iif[j] = (float)ii[j]; }
+    const float* R = rots + 9 * c;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)        // fp32 matmul of the fp32 inverse, as rots.matmul(torch.inverse(intrins))
+            combine[9 * c + 3 * r + k] = fmaf(R[3 * r + 2], iif[6 + k], fmaf(R[3 * r + 1], iif[3 + k], R[3 * r] * iif[k]));
+}
+
+extern "C" int heal_lss_camera_matrices(const float* rots, const float* intrins, const float* post_rots, int num_images,
+                                        float* post_rots_inv_out, float* combine_out, void* stream_) {
+    if (!rots || !intrins || !post_rots || !post_rots_inv_out || !combine_out) return HEAL_ERR_ARG;
+    if (num_images <= 0) return HEAL_OK;
+    k_lss_camera_matrices<<<(num_images + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(rots, intrins, post_rots, num_images,
+                                                                                   post_rots_inv_out, combine_out);
+    return heal_check_launch();
+}
+
 extern "C" int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,
                                    const float* post_rots_inv, const float* post_trans, const float* combine, const float* trans,
                                    int num_images, const float* lower3_host, const float* dx3_host, const int* nx3_host,

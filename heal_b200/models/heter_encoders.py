@@ -233,8 +233,7 @@ class LiftSplatShoot(nn.Module):
     def bev_from_heads(self, depth_logits, feat, rots, trans, intrins, post_rots, post_trans):
         """The kernel part: geometry -> cell index -> fused softmax (x) feat -> BEV pool.  Returns Act f32 (B,ny,nx,C)."""
         B, N = trans.shape[:2]
-        post_inv = torch.inverse(post_rots).reshape(B * N, 3, 3)          # 3x3 algebra exactly as the reference (:135,:142)
-        combine = rots.matmul(torch.inverse(intrins)).reshape(B * N, 3, 3)
+        post_inv, combine = ops.lss_camera_matrices(rots, intrins, post_rots)      # the reference's 3x3 algebra (:135,:142), capturable
         lower = (self.bx - self.dx / 2.).tolist()
         cell = ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
                                   lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
@@ -242,8 +241,7 @@ class LiftSplatShoot(nn.Module):
 
     def cell_index(self, rots, trans, intrins, post_rots, post_trans):
         B, N = trans.shape[:2]
-        post_inv = torch.inverse(post_rots).reshape(B * N, 3, 3)          # 3x3 algebra exactly as the reference (:135,:142)
-        combine = rots.matmul(torch.inverse(intrins)).reshape(B * N, 3, 3)
+        post_inv, combine = ops.lss_camera_matrices(rots, intrins, post_rots)      # the reference's 3x3 algebra (:135,:142), capturable
         lower = (self.bx - self.dx / 2.).tolist()
         return ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
                                   lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])

@@ -674,6 +674,17 @@ def att_fuse(feat: Act, theta: torch.Tensor, out: Optional[Act] = None, out_fmt:
 # ------------------------------------------------------------------------------------------------
 # Lift-Splat-Shoot
 # ------------------------------------------------------------------------------------------------
+def lss_camera_matrices(rots, intrins, post_rots):
+    """(…,3,3) f32 each -> (post_rots^-1, rots @ intrins^-1) as (BN,3,3) f32; one capturable launch (torch.inverse is not)."""
+    _need_cuda(rots, intrins, post_rots)
+    r = rots.reshape(-1, 3, 3).contiguous().float()
+    k = intrins.reshape(-1, 3, 3).contiguous().float()
+    pr = post_rots.reshape(-1, 3, 3).contiguous().float()
+    post_inv, combine = torch.empty_like(pr), torch.empty_like(r)
+    check(lib.heal_lss_camera_matrices(_p(r), _p(k), _p(pr), r.shape[0], _p(post_inv), _p(combine), _stream()), "heal_lss_camera_matrices")
+    return post_inv, combine
+
+
 def lss_cell_index(frustum, post_rots_inv, post_trans, combine, trans, lower, dx, nx) -> torch.Tensor:
     """frustum (D,fH,fW,3); per-image 3x3 / 3-vectors (BN,...) -> int32 (BN,D,fH,fW) BEV cell or -1."""
     _need_cuda(frustum, post_rots_inv, post_trans, combine, trans)
@@ -1091,7 +1102,7 @@ def _guard(fn):
 
 
 for _name in ("mask_points", "dwconv_layernorm", "maxpool3x3s2", "convert", "voxelize", "mean_vfe", "pillar_vfe_scatter", "pillar_scatter", "conv2d_simt", "conv2d_tc", "pyramid_fuse_level", "att_fuse",
-              "lss_cell_index", "lss_pool", "lss_pool_sorted", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
+              "lss_camera_matrices", "lss_cell_index", "lss_pool", "lss_pool_sorted", "sp_build_table", "sp_subm_neighbors", "sp_strided", "sp_gather_gemm", "sp_gather_gemm_tc", "rows_to_split", "sparse_to_bev",
               "pillar_vfe_sparse", "sparse_stem", "box_decode_nms"):
     globals()[_name] = _guard(globals()[_name])
 

@@ -180,6 +180,10 @@ int heal_att_fuse(const heal_act_t* feat, const double* theta, int n_agents, int
  * (opencood/models/sub_modules/lss_submodule.py:132-134, :227-229) and voxel_pooling's per-cell sum
  * (heter_encoders.py:188-212): bev_out (agents, nz*ny*nx, C) channels-last fp32, pre-zeroed (nz == 1 gives
  * the reference's (B,C,ny,nx) map). depth_logits (BN,D,fH,fW), feat (BN,C,fH,fW) as the torch heads emit them. */
+/* per-camera 3x3 algebra of get_geometry (heter_encoders.py:135,142), capturable in a CUDA graph (torch.inverse is not):
+ * post_rots_inv_out = inverse(post_rots), combine_out = rots @ inverse(intrins); all (num_images,3,3) f32 row-major, device. */
+int heal_lss_camera_matrices(const float* rots, const float* intrins, const float* post_rots, int num_images,
+                             float* post_rots_inv_out, float* combine_out, void* stream);
 int heal_lss_cell_index(const float* frustum, int D, int fH, int fW,
                         const float* post_rots_inv, const float* post_trans, const float* combine, const float* trans,
                         int num_images, const float* lower3_host, const float* dx3_host, const int* nx3_host,

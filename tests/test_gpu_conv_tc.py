@@ -150,3 +150,73 @@ def test_conv_tc_stride_grouped(case):
     err = (got - y).abs().max().item()
     print(f"{name}: max|y|={y.abs().max().item():.3f} err={err:.3e}")
     assert err < 1e-3
+
+
+RING_CASES = [
+    # name, N, C, H, W, groups  -> strips x row segments (conv3x3_ring.cu): multi-segment, ragged last segment, one-row segments
+    ("ring_cg4_w256_h37", 3, 128, 37, 256, 32),       # 12 strips x 8 segments of 5 rows (last: 2)
+    ("ring_cg8_w128_h64", 5, 256, 64, 128, 32),       # 20 strips x 7 segments of 10 rows (last: 4)
+    ("ring_cg4_w128_h5", 1, 128, 5, 128, 32),         # 2 strips, 1 segment: fewer rows than ring slots + 1
+    ("ring_cg16_w128_h130", 1, 512, 130, 128, 32),    # 8 strips x 18 segments
+]
+
+
+@pytest.mark.parametrize("case", RING_CASES, ids=[c[0] for c in RING_CASES])
+@pytest.mark.parametrize("planes", [2, 1], ids=["tc32", "bf16"])
+def test_grouped_conv_row_ring(case, planes):
+    """Grouped 3x3 on maps >= 128 wide runs the row-ring kernel: vs fp32 PyTorch on the CPU, and written into a channel slice of a
+    wider buffer (the neighbours must stay untouched)."""
+    from heal_b200 import ops
+    name, N, C, H, W, groups = case
+    gen = torch.Generator().manual_seed(abs(hash(name)) % 10000)
+    conv = torch.nn.Conv2d(C, C, 3, padding=1, groups=groups, bias=False)
+    bnm = torch.nn.BatchNorm2d(C, eps=1e-5).eval()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * (1.0 / (C // groups * 9)) ** 0.5)
+        bnm.weight.copy_(torch.rand(C, generator=gen) + 0.5)
+        bnm.bias.copy_(torch.randn(C, generator=gen) * 0.1)
+        bnm.running_mean.copy_(torch.randn(C, generator=gen) * 0.1)
+        bnm.running_var.copy_(torch.rand(C, generator=gen) + 0.5)
+    x = torch.randn(N, C, H, W, generator=gen)
+    with torch.no_grad():
+        y = F.relu(bnm(conv(x)))
+    fmt = "split" if planes == 2 else "bf16"
+    pc = ops.pack_conv_tc(conv, bnm, True, planes=2).to("cuda")
+    xs = ops.convert(ops.to_act(x.cuda()), fmt)
+    o, _ = ops.conv2d_tc(xs, pc)
+    buf = torch.zeros((planes, N, H, W, C + 128), dtype=torch.bfloat16, device="cuda")
+    ops.conv2d_tc(xs, pc, out=ops.Act(buf, fmt), out_coffset=64)
+    torch.cuda.synchronize()
+    got = ops.act_to_nchw(o).cpu()
+    scale = max(y.abs().max().item(), 1.0)
+    err = (got - y).abs().max().item()
+    print(f"{name} planes={planes}: max|y|={scale:.3f} err={err:.3e}")
+    assert err < (1e-3 if planes == 2 else 1.4e-2 * scale)
+    assert torch.equal(buf[..., 64:64 + C], o.t) and torch.all(buf[..., :64] == 0) and torch.all(buf[..., 64 + C:] == 0)
+
+
+def test_grouped_conv_row_ring_equals_tile_kernel(monkeypatch):
+    """Same MMAs in the same order per output element: the ring kernel and the tile-per-CTA kernel agree bit for bit
+    (HEAL_TC_RING is read once per process, so the tile kernel runs in a child process)."""
+    import os, subprocess, sys, tempfile
+    from heal_b200 import ops
+    code = (
+        "import sys, torch\n"
+        "from heal_b200 import ops\n"
+        "g = torch.Generator().manual_seed(5)\n"
+        "conv = torch.nn.Conv2d(128, 128, 3, padding=1, groups=32, bias=False)\n"
+        "conv.weight.data.copy_(torch.randn(conv.weight.shape, generator=g) / 6)\n"
+        "x = torch.randn(2, 128, 21, 256, generator=g)\n"
+        "pc = ops.pack_conv_tc(conv, None, True, planes=2).to('cuda')\n"
+        "o, _ = ops.conv2d_tc(ops.convert(ops.to_act(x.cuda()), 'split'), pc)\n"
+        "torch.cuda.synchronize()\n"
+        "torch.save(o.t.cpu(), sys.argv[1])\n")
+    outs = []
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        for ring in ("1", "0"):
+            path = os.path.join(td, f"o{ring}.pt")
+            env = dict(os.environ, HEAL_TC_RING=ring, PYTHONPATH=root)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300, cwd=root)
+            outs.append(torch.load(path))
+    assert torch.equal(outs[0], outs[1])

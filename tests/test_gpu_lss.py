@@ -150,3 +150,51 @@ def test_lift_splat_shoot_voxel_equals_lss_for_single_slice_grid():
     with torch.no_grad():
         ya, yb = a(dd, "m2"), b(dd, "m2")
     assert ya.shape == (1, 32, 64, 64) and torch.equal(ya, yb)
+
+
+def test_camera_matrices_vs_torch_inverse_and_graph_capture():
+    """heal_lss_camera_matrices == (inverse(post_rots), rots @ inverse(intrins)) to fp32 rounding, and the whole LSS encoder
+    (trunk, heads, camera algebra, cell index, sorted pooling) captures into a CUDA graph whose replay equals the eager forward."""
+    from heal_b200 import engine, ops, synth
+    from heal_b200.models.heter_encoders import LiftSplatShoot
+    from oracle import make_golden
+    from workloads import procedural
+    rots, trans, intr, post_rots, post_trans = [torch.from_numpy(v) for v in synth.camera_rig(2, 4, 256, 704)]
+    pi, cb = ops.lss_camera_matrices(rots.cuda(), intr.cuda(), post_rots.cuda())
+    pi_ref = torch.inverse(post_rots.double()).reshape(-1, 3, 3)
+    cb_ref = rots.double().matmul(torch.inverse(intr.double())).reshape(-1, 3, 3)
+    assert (pi.cpu().double() - pi_ref).abs().max() <= 2e-7 * pi_ref.abs().max()
+    assert (cb.cpu().double() - cb_ref).abs().max() <= 4e-7 * cb_ref.abs().max()
+    # same cells as with torch.inverse's fp32 LU except frustum points on a cell boundary
+    engine.set_precision("bf16")
+    try:
+        cfg = make_golden.lss_small_cfg()
+        m = LiftSplatShoot(dict(cfg)).eval()
+        m.load_state_dict(procedural.make_state_dict(procedural.shapes_of(m)), strict=True)
+        m = m.cuda()
+        r2, t2, k2, pr2, pt2 = [torch.from_numpy(v).cuda() for v in synth.camera_rig(1, 2, 64, 128)]
+        cell = m.cell_index(r2, t2, k2, pr2, pt2)
+        lower = (m.bx - m.dx / 2.).tolist()
+        cell_t = ops.lss_cell_index(m.frustum, torch.inverse(pr2).reshape(-1, 3, 3), pt2.reshape(-1, 3),
+                                    r2.matmul(torch.inverse(k2)).reshape(-1, 3, 3), t2.reshape(-1, 3), lower, m.dx.tolist(),
+                                    [int(v) for v in m.nx.tolist()])
+        assert (cell != cell_t).float().mean().item() < 2e-4
+        imgs = torch.randn(1, 2, 3, 64, 128, generator=torch.Generator().manual_seed(8)).cuda()
+        dd = {"inputs_m2": {"imgs": imgs, "rots": r2, "trans": t2, "intrins": k2, "post_rots": pr2, "post_trans": pt2}}
+        with torch.no_grad():
+            eager = m(dd, "m2").clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m(dd, "m2")
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = m(dd, "m2")
+            imgs.normal_()          # the graph reads the static input buffers: new images, same graph
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, m(dd, "m2")) and not torch.equal(out, eager)
+    finally:
+        engine.set_precision("tc32")
