@@ -762,7 +762,7 @@ def run_gpu(opt):
             mma_per_flop = 3 if (opt.precision == "tc32" and tc) else 1
             tj, tname = load_ncu_traffic()
             traffic = tj.get("k_conv2d_tc_bytes_per_launch") if tc else None
-            roofline = {"bound": "tensor", "kernel": "k_conv2d_tc (tcgen05 implicit-GEMM conv: 1x1/3x3/grouped/strided/transposed)"
+            roofline = {"bound": "tensor", "kernel": "k_conv2d_tc + k_gconv3x3_ring (tcgen05 implicit-GEMM conv: 1x1/3x3/grouped/strided/transposed)"
                         if tc else "k_conv2d_dense/grouped (fp32 CUDA cores)",
                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if ach else None,
                         "traffic": traffic, "traffic_source": f"profiles/{tname}" if traffic else None, "peak_source": peak_src,
@@ -815,6 +815,7 @@ def run_gpu(opt):
                 eager_ref = cuda_eager_leg(wl_name, n_agents, scenes, dev, ref_out)
             except Exception as e:
                 eager_ref = {"error": repr(e)[:300]}
+        graphed = fg is not None or getattr(wl, "graph", None) is not None
         secondary = None
         e2e_mode = ("FramePipeline: 2 captured frames, copy-in / compute / copy-out streams" if pipe is not None
                     else "single stream: H2D -> frame -> D2H")
@@ -842,7 +843,7 @@ def run_gpu(opt):
                 "postprocess": post, "other_workloads": secondary,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "gflop_per_frame": frame_flops(n_agents) / 1e9 if is_pyramid_lidar else None}
-        if fg is None and getattr(wl, "graph", None) is None:
+        if not graphed:
             line["config"]["launch"] = "eager launches, one stream (no CUDA graph: --no-graph or the capture failed, see stderr)"
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

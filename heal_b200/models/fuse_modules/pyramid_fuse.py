@@ -58,6 +58,13 @@ class PyramidFusion(ResNetBEVBackbone):
 
     def _crop_windows(self, H, W, agent_modality_list, cam_crop_info, device):
         """(sumN,4) int32 [h0,h1,w0,w1] per agent: region where the score survives (pyramid_fuse.py:147-162)."""
+        # static per (map size, modality list): built once and kept on the device (a host->device copy per frame would also be
+        # rejected by a CUDA graph capture)
+        key = (H, W, tuple(agent_modality_list), str(device))
+        cache = self.__dict__.setdefault("_crop_window_cache", {})
+        if key in cache:
+            return cache[key]
+
         def clamp(s, e, n):   # python slice semantics of [s:e] on a length-n axis
             s = max(n + s, 0) if s < 0 else min(s, n)
             e = max(n + e, 0) if e < 0 else min(e, n)
@@ -72,7 +79,8 @@ class PyramidFusion(ResNetBEVBackbone):
                 win.append([sh, eh, sw, ew])
             else:
                 win.append([0, H, 0, W])
-        return torch.tensor(win, dtype=torch.int32, device=device)
+        cache[key] = torch.tensor(win, dtype=torch.int32, device=device)
+        return cache[key]
 
     def forward_collab_nhwc(self, x, record_len, affine_matrix, agent_modality_list=None, cam_crop_info=None):
         """x: Act (sumN,H,W,C) -> (fused Act (B,H,W,sum C_up), [occ Act f32 (sumN,h,w,1)] per level)."""

@@ -206,6 +206,11 @@ class LiftSplatShoot(nn.Module):
         self.register_buffer("dx", dx.clone(), persistent=False)
         self.register_buffer("bx", bx.clone(), persistent=False)
         self.register_buffer("nx", nx.clone(), persistent=False)
+        # host copies of the grid constants: the kernels take them as host arguments, and reading the (device) buffers back would
+        # be a synchronising copy per frame that a CUDA graph capture rejects
+        self._lower_host = (bx - dx / 2.).tolist()
+        self._dx_host = dx.tolist()
+        self._nx_host = [int(v) for v in nx.tolist()]
         self.depth_supervision = args['depth_supervision']
         self.downsample = args['img_downsample']
         self.camC = args['img_features']
@@ -217,7 +222,7 @@ class LiftSplatShoot(nn.Module):
                                       "use 'Resnet101' (SURVEY.md 8c)")
         self.camencode = CamEncode_Resnet101(self.D, self.camC, self.downsample, self.grid_conf['ddiscr'],
                                              self.grid_conf['mode'], args['use_depth_gt'], args['depth_supervision'])
-        if int(self.nx[2]) != 1:
+        if self._nx_host[2] != 1:
             raise NotImplementedError("heal_lss_pool supports a single z slice (every HEAL yaml uses zbound with nz == 1)")
 
     def create_frustum(self):
@@ -234,17 +239,15 @@ class LiftSplatShoot(nn.Module):
         """The kernel part: geometry -> cell index -> fused softmax (x) feat -> BEV pool.  Returns Act f32 (B,ny,nx,C)."""
         B, N = trans.shape[:2]
         post_inv, combine = ops.lss_camera_matrices(rots, intrins, post_rots)      # the reference's 3x3 algebra (:135,:142), capturable
-        lower = (self.bx - self.dx / 2.).tolist()
         cell = ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
-                                  lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
-        return ops.lss_pool(depth_logits, feat, cell, N, int(self.nx[0]), int(self.nx[1]))
+                                  self._lower_host, self._dx_host, self._nx_host)
+        return ops.lss_pool(depth_logits, feat, cell, N, self._nx_host[0], self._nx_host[1])
 
     def cell_index(self, rots, trans, intrins, post_rots, post_trans):
         B, N = trans.shape[:2]
         post_inv, combine = ops.lss_camera_matrices(rots, intrins, post_rots)      # the reference's 3x3 algebra (:135,:142), capturable
-        lower = (self.bx - self.dx / 2.).tolist()
         return ops.lss_cell_index(self.frustum, post_inv, post_trans.reshape(B * N, 3), combine, trans.reshape(B * N, 3),
-                                  lower, self.dx.tolist(), [int(v) for v in self.nx.tolist()])
+                                  self._lower_host, self._dx_host, self._nx_host)
 
     def forward_act(self, data_dict, modality_name, fmt=None):
         """image trunk + heads on the conv engine -> frustum cell index -> deterministic sorted BEV pooling
@@ -266,7 +269,7 @@ class LiftSplatShoot(nn.Module):
             self.depth_items = (y.t[..., :D].permute(0, 3, 1, 2), None)
         cell = self.cell_index(d['rots'], d['trans'], d['intrins'], d['post_rots'], d['post_trans'])
         return ops.lss_pool_sorted(y.t, (HW * S, 1, S), y.t[..., D:], (HW * S, 1, S), cell, N, D, camC, fH, fW,
-                                   int(self.nx[0]), int(self.nx[1]), out_fmt=fmt or act_fmt())
+                                   self._nx_host[0], self._nx_host[1], out_fmt=fmt or act_fmt())
 
     def forward(self, data_dict, modality_name):
         return ops.act_to_nchw(self.forward_act(data_dict, modality_name))

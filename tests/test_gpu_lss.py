@@ -174,10 +174,9 @@ def test_camera_matrices_vs_torch_inverse_and_graph_capture():
         m = m.cuda()
         r2, t2, k2, pr2, pt2 = [torch.from_numpy(v).cuda() for v in synth.camera_rig(1, 2, 64, 128)]
         cell = m.cell_index(r2, t2, k2, pr2, pt2)
-        lower = (m.bx - m.dx / 2.).tolist()
         cell_t = ops.lss_cell_index(m.frustum, torch.inverse(pr2).reshape(-1, 3, 3), pt2.reshape(-1, 3),
-                                    r2.matmul(torch.inverse(k2)).reshape(-1, 3, 3), t2.reshape(-1, 3), lower, m.dx.tolist(),
-                                    [int(v) for v in m.nx.tolist()])
+                                    r2.matmul(torch.inverse(k2)).reshape(-1, 3, 3), t2.reshape(-1, 3), m._lower_host, m._dx_host,
+                                    m._nx_host)
         assert (cell != cell_t).float().mean().item() < 2e-4
         imgs = torch.randn(1, 2, 3, 64, 128, generator=torch.Generator().manual_seed(8)).cuda()
         dd = {"inputs_m2": {"imgs": imgs, "rots": r2, "trans": t2, "intrins": k2, "post_rots": pr2, "post_trans": pt2}}
