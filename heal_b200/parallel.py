@@ -195,6 +195,25 @@ class SymmetricExchange:
 
     N_BARRIERS = 4
 
+    @staticmethod
+    def usable(device, group=None) -> bool:
+        """True when EVERY rank of the group can allocate symmetric memory (checked before the collective rendezvous, so a rank
+        without support cannot leave the others waiting): the `comm="auto"` choice between the P2P push and NCCL."""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            g = group if group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(g.group_name)
+            except Exception:
+                pass
+            symm_mem.empty(256, dtype=torch.uint8, device=device)
+        except Exception:
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        return int(t.item()) == 1
+
     def __init__(self, nbytes: int, device, group=None):
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
@@ -286,7 +305,7 @@ class AgentShardedFrame:
         self.n_head = model.cls_head.out_channels + model.reg_head.out_channels + model.dir_head.out_channels
         head_bytes = self.Hf * self.Wf * self.n_head * 4
         if comm == "auto":
-            comm = "p2p" if world > 1 else "nccl"
+            comm = "p2p" if (world > 1 and SymmetricExchange.usable(dev, group)) else "nccl"
         self.comm = comm
         nsides = 2 if (comm == "p2p" and world > 1) else 1
         gather_bytes = world * self.chunk
