@@ -559,7 +559,7 @@ struct TcEnv {
     int dbg, pdl, halo, bo, tma_store, res_tma, ring;
     TcEnv() {
         auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
-        dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 0); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
+        dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 1); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
         tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1);
     }
 };
@@ -760,7 +760,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         coutp == Cout && !p.dbg) {
         RingP rp;
         rp.N = N; rp.H = Ho; rp.W = Wo; rp.C = Cout; rp.planes = planes; rp.wplanes = w_planes; rp.relu = relu; rp.bias = bias;
-        rp.segs = 1; rp.seg_rows = Ho;
+        rp.segs = 1; rp.seg_rows = Ho; rp.pdl = env.pdl;
         return heal_conv3x3_ring_launch(tmA, tmB, tmO, rp, st);
     }
     if (relu == 2) {        // GELU: 1x1 / 3x3 convs with >= 128 output channels and no residual (ConvNeXt pwconv1: dim -> 4 dim)

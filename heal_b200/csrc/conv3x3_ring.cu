@@ -82,6 +82,12 @@ k_gconv3x3_ring(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const bool split = (p.planes == 2), wsplit = (p.wplanes == 2);
+    // programmatic dependent launch: barrier init / TMEM allocation above overlapped the previous kernel's tail; nothing it
+    // produced has been touched yet
+    if (p.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -233,6 +239,17 @@ int heal_conv3x3_ring_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     p.segs = (p.H + p.seg_rows - 1) / p.seg_rows;
     static size_t attr_set[HEAL_MAX_DEVICES] = {};
     if (!heal_ensure_dyn_smem(k_gconv3x3_ring, RG_SMEM_LIMIT, attr_set)) return HEAL_ERR_LAUNCH;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(strips * p.segs); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_gconv3x3_ring, tmA, tmB, tmO, p, slots);
+        heal_launch_counter_add(1);
+        return e == cudaSuccess ? HEAL_OK : HEAL_ERR_LAUNCH;
+    }
     k_gconv3x3_ring<<<strips * p.segs, RG_THREADS, smem, st>>>(tmA, tmB, tmO, p, slots);
     return heal_check_launch();
 }

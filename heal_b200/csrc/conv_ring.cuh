@@ -8,6 +8,7 @@ struct RingP {
     int planes, wplanes;     // activation / weight bf16 planes (1 or 2)
     int relu;                // 0 none, 1 ReLU
     int segs, seg_rows;      // row segments per (image, column tile, channel block) strip and rows per segment
+    int pdl;                 // launched with programmatic stream serialization (griddepcontrol.wait before the first global read)
     const float* bias;       // [C] or null
 };
 

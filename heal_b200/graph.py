@@ -94,9 +94,50 @@ class FrameGraph:
         return self.out
 
 
+class FrameInterleaver:
+    """N captured frames, each on its own stream: consecutive frames overlap on the GPU (the small latency-bound kernels at the
+    head of frame i+1 -- voxeliser, VFE, stem -- and the tails / prologues of its convolutions run in the gaps of frame i).  A
+    throughput device for streams of independent frames; the latency of one frame is that of a single FrameGraph or worse.
+
+        il = FrameInterleaver(model, n_agents, point_capacity, pairwise_shape, n=2)
+        out = il.submit(points, offsets, pairwise)     # device tensors of frame i; `out` is complete after il.wait(slot)
+    """
+
+    def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, n: int = 2, modality: str = "m1", device=None):
+        dev = device or next(model.parameters()).device
+        self.dev, self.n = dev, n
+        self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(n)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        self.count = 0
+        self.join(begin=True)
+
+    @property
+    def kernels_per_replay(self):
+        return self.graphs[0].kernels_per_replay
+
+    def submit(self, points, offsets, pairwise):
+        k = self.count % self.n
+        with torch.cuda.stream(self.streams[k]):        # the previous use of slot k is earlier on the same stream
+            self.graphs[k].load(points, offsets, pairwise)
+            out = self.graphs[k].replay()
+        self.count += 1
+        return out
+
+    def join(self, begin: bool):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            if begin:
+                s.wait_stream(cur)
+            else:
+                cur.wait_stream(s)
+
+
 class FramePipeline:
-    """Two captured frames on three streams: while frame i computes, frame i+1's inputs are copied in (pinned host -> HBM) and
-    frame i-1's predictions are copied out (HBM -> pinned host).  The serving loop's public entry point:
+    """Two captured frames on four streams: while frame i computes, frame i+1's inputs are copied in (pinned host -> HBM), frame
+    i-1's predictions are copied out (HBM -> pinned host), and -- each frame slot replays on its OWN compute stream -- the head of
+    frame i+1 (voxeliser, VFE, stem: small latency-bound kernels) runs in the gaps of frame i's convolutions (measured +10 %
+    frames/s over one compute stream; `compute_streams=1` restores strict frame-after-frame execution).  The serving loop's
+    public entry point:
 
         pipe = FramePipeline(model, n_agents, point_capacity, pairwise_shape)
         preds = pipe.submit(points_pinned, offsets_pinned, pairwise_pinned)   # dict of pinned host tensors of frame i - 1 (or None)
@@ -107,11 +148,14 @@ class FramePipeline:
 
     OUT_KEYS = ("cls_preds", "reg_preds", "dir_preds")
 
-    def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, modality: str = "m1", device=None):
+    def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, modality: str = "m1", device=None,
+                 compute_streams: int = 2):
         dev = device or next(model.parameters()).device
         self.dev = dev
         self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(2)]
-        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.s_in, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(2))
+        comp = [torch.cuda.Stream(device=dev) for _ in range(2 if compute_streams >= 2 else 1)]
+        self.s_comp = [comp[0], comp[-1]]                     # compute stream of frame slot 0 / 1
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_comp = [torch.cuda.Event() for _ in range(2)]
         self.ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -121,7 +165,7 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
         cur = torch.cuda.current_stream(dev)
-        for s in (self.s_in, self.s_comp, self.s_out):
+        for s in (self.s_in, *self.s_comp, self.s_out):
             s.wait_stream(cur)
 
     def submit(self, points: torch.Tensor, offsets: torch.Tensor, pairwise: torch.Tensor):
@@ -133,12 +177,13 @@ class FramePipeline:
                 self.s_in.wait_event(self.ev_comp[k])          # frame count-2 has consumed these input buffers
             g.load(points, offsets, pairwise)
             self.ev_in[k].record(self.s_in)
-        with torch.cuda.stream(self.s_comp):
-            self.s_comp.wait_event(self.ev_in[k])
+        sc = self.s_comp[k]
+        with torch.cuda.stream(sc):
+            sc.wait_event(self.ev_in[k])
             if self.count >= 2:
-                self.s_comp.wait_event(self.ev_out[k])         # its predictions have left the output buffers
+                sc.wait_event(self.ev_out[k])                  # its predictions have left the output buffers
             g.replay()
-            self.ev_comp[k].record(self.s_comp)
+            self.ev_comp[k].record(sc)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[k])
             for name, h in self.host_out[k].items():
@@ -162,7 +207,7 @@ class FramePipeline:
     def join(self, begin: bool):
         """Order the pipeline's streams after (begin) / before (end) the caller's current stream, e.g. around timing events."""
         cur = torch.cuda.current_stream(self.dev)
-        for s in (self.s_in, self.s_comp, self.s_out):
+        for s in (self.s_in, *self.s_comp, self.s_out):
             if begin:
                 s.wait_stream(cur)
             else:
