@@ -207,3 +207,30 @@ def test_frame_graph_and_pipeline_equal_eager():
     for i in range(len(scenes)):
         for k in keys:
             assert torch.equal(got[i][k], eager[i][k]), (i, k)
+    # strict frame-after-frame variant of the pipeline, and N frames in flight on N streams (bench.py's `value`)
+    pipe1 = FramePipeline(model, 3, cap, tuple(scenes[0][2].shape), compute_streams=1)
+    got1 = []
+    for p, o, pw in scenes:
+        prev = pipe1.submit(p, o, pw)
+        if prev is not None:
+            got1.append({k: prev[k].clone() for k in keys})
+    got1.append({k: pipe1.flush()[k].clone() for k in keys})
+    from heal_b200.graph import FrameInterleaver
+    dev_scenes = [tuple(t.cuda() for t in sc) for sc in scenes]
+    for n in (2, 3):
+        il = FrameInterleaver(model, 3, cap, tuple(scenes[0][2].shape), n=n)
+        outs = []
+        for rep in range(2):                      # slots are reused: the second pass runs behind the first on the same streams
+            for i, (p, o, pw) in enumerate(dev_scenes):
+                out = il.submit(p, o, pw)
+                if i >= len(dev_scenes) - n and rep == 1:
+                    outs.append((i, out))        # the last n frames still own their slots when the queue drains
+        il.join(begin=False)
+        torch.cuda.synchronize()
+        assert len(outs) == n
+        for i, out in outs:
+            for k in keys:
+                assert torch.equal(out[k].cpu(), eager[i][k]), (n, i, k)
+    for i in range(len(scenes)):
+        for k in keys:
+            assert torch.equal(got1[i][k], eager[i][k]), (i, k)
