@@ -570,6 +570,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["tc32", "bf16", "fp32"], help="default tc32 (bf16 for --workload c4)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--inflight", type=int, default=2, help="captured frames in flight for `value` (N graphs on N streams, heal_b200.graph.FrameInterleaver); 1 = strictly one frame after the other (the number reported as `latency`)")
+    ap.add_argument("--pipeline-depth", type=int, default=3, help="e2e: captured frames in flight in FramePipeline (results are delivered depth-1 submits later)")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one stream, H2D -> frame -> D2H back to back (no copy/compute overlap)")
     opt = ap.parse_args()
     ref = opt.impl == "reference"
@@ -710,7 +711,7 @@ def run_gpu(opt):
         pipe = None
         if fg is not None and not opt.no_pipeline:
             from heal_b200.graph import FramePipeline
-            pipe = FramePipeline(model, n_agents, fg.capacity, scenes[0]["pairwise"].shape)
+            pipe = FramePipeline(model, n_agents, fg.capacity, scenes[0]["pairwise"].shape, depth=opt.pipeline_depth)
         h2d = d2h = 0
 
         def frame_pipe(i):
@@ -856,7 +857,7 @@ def run_gpu(opt):
                 eager_ref = {"error": repr(e)[:300]}
         graphed = fg is not None or getattr(wl, "graph", None) is not None
         secondary = None
-        e2e_mode = ("FramePipeline: 2 captured frames in flight; copy-in, copy-out and one compute stream per frame slot" if pipe is not None
+        e2e_mode = (f"FramePipeline(depth={opt.pipeline_depth}): captured frames in flight; copy-in, copy-out and two alternating compute streams" if pipe is not None
                     else "single stream: H2D -> frame -> D2H")
         if world == 1 and wl_name == "c2" and not opt.no_secondary:
             secondary = {}

@@ -149,38 +149,42 @@ class FramePipeline:
     OUT_KEYS = ("cls_preds", "reg_preds", "dir_preds")
 
     def __init__(self, model, n_agents: int, point_capacity: int, pairwise_shape, modality: str = "m1", device=None,
-                 compute_streams: int = 2):
+                 compute_streams: int = 2, depth: int = 2):
+        """`depth` = captured frames (slots) in flight: `submit` of frame i returns the predictions of frame i - (depth - 1).
+        depth 2 keeps one frame queued behind the running one; depth 3 keeps the GPU's two compute streams fed while the host
+        waits for a result (+3 % frames/s, one more frame of delivery delay)."""
         dev = device or next(model.parameters()).device
-        self.dev = dev
-        self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(2)]
+        self.dev, self.depth = dev, max(2, int(depth))
+        self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(self.depth)]
         self.s_in, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(2))
         comp = [torch.cuda.Stream(device=dev) for _ in range(2 if compute_streams >= 2 else 1)]
-        self.s_comp = [comp[0], comp[-1]]                     # compute stream of frame slot 0 / 1
-        self.ev_in = [torch.cuda.Event() for _ in range(2)]
-        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.s_comp = [comp[k % len(comp)] for k in range(self.depth)]     # compute stream of each frame slot
+        self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.depth)]
         self.host_out = [{k: torch.empty(g.out[k].shape, dtype=g.out[k].dtype).pin_memory() for k in self.OUT_KEYS if k in g.out}
                          for g in self.graphs]
         self.count = 0
         self.h2d_bytes = 0
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
         cur = torch.cuda.current_stream(dev)
-        for s in (self.s_in, *self.s_comp, self.s_out):
+        for s in (self.s_in, *set(self.s_comp), self.s_out):
             s.wait_stream(cur)
 
     def submit(self, points: torch.Tensor, offsets: torch.Tensor, pairwise: torch.Tensor):
-        k = self.count & 1
+        d = self.depth
+        k = self.count % d
         g = self.graphs[k]
         prev = None
         with torch.cuda.stream(self.s_in):
-            if self.count >= 2:
-                self.s_in.wait_event(self.ev_comp[k])          # frame count-2 has consumed these input buffers
+            if self.count >= d:
+                self.s_in.wait_event(self.ev_comp[k])          # frame count-depth has consumed these input buffers
             g.load(points, offsets, pairwise)
             self.ev_in[k].record(self.s_in)
         sc = self.s_comp[k]
         with torch.cuda.stream(sc):
             sc.wait_event(self.ev_in[k])
-            if self.count >= 2:
+            if self.count >= d:
                 sc.wait_event(self.ev_out[k])                  # its predictions have left the output buffers
             g.replay()
             self.ev_comp[k].record(sc)
@@ -189,25 +193,34 @@ class FramePipeline:
             for name, h in self.host_out[k].items():
                 h.copy_(g.out[name], non_blocking=True)
             self.ev_out[k].record(self.s_out)
-        if self.count >= 1:
-            self.ev_out[k ^ 1].synchronize()                   # frame count-1 is complete on the host
-            prev = self.host_out[k ^ 1]
+        if self.count >= d - 1:
+            j = (self.count - (d - 1)) % d
+            self.ev_out[j].synchronize()                       # frame count-(depth-1) is complete on the host
+            prev = self.host_out[j]
         self.h2d_bytes = points.numel() * points.element_size() + offsets.numel() * offsets.element_size() \
             + pairwise.numel() * pairwise.element_size()
         self.count += 1
         return prev
 
+    def drain(self):
+        """Predictions of the frames still in flight, oldest first (the results `submit` has not returned yet)."""
+        out = []
+        for c in range(max(self.count - (self.depth - 1), 0), self.count):
+            self.ev_out[c % self.depth].synchronize()
+            out.append(self.host_out[c % self.depth])
+        return out
+
     def flush(self):
+        """Wait for everything in flight; returns the LAST frame's predictions."""
         if self.count == 0:
             return None
-        k = (self.count - 1) & 1
-        self.ev_out[k].synchronize()
-        return self.host_out[k]
+        res = self.drain()
+        return res[-1]
 
     def join(self, begin: bool):
         """Order the pipeline's streams after (begin) / before (end) the caller's current stream, e.g. around timing events."""
         cur = torch.cuda.current_stream(self.dev)
-        for s in (self.s_in, *self.s_comp, self.s_out):
+        for s in (self.s_in, *set(self.s_comp), self.s_out):
             if begin:
                 s.wait_stream(cur)
             else:

@@ -215,6 +215,17 @@ def test_frame_graph_and_pipeline_equal_eager():
         if prev is not None:
             got1.append({k: prev[k].clone() for k in keys})
     got1.append({k: pipe1.flush()[k].clone() for k in keys})
+    pipe3 = FramePipeline(model, 3, cap, tuple(scenes[0][2].shape), depth=3)        # results come back two submits later
+    got3 = []
+    for p, o, pw in scenes:
+        prev = pipe3.submit(p, o, pw)
+        if prev is not None:
+            got3.append({k: prev[k].clone() for k in keys})
+    got3 += [{k: r[k].clone() for k in keys} for r in pipe3.drain()]
+    assert len(got3) == len(scenes)
+    for i in range(len(scenes)):
+        for k in keys:
+            assert torch.equal(got3[i][k], eager[i][k]), ("depth3", i, k)
     from heal_b200.graph import FrameInterleaver
     dev_scenes = [tuple(t.cuda() for t in sc) for sc in scenes]
     for n in (2, 3):
