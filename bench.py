@@ -570,7 +570,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["tc32", "bf16", "fp32"], help="default tc32 (bf16 for --workload c4)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--inflight", type=int, default=2, help="captured frames in flight for `value` (N graphs on N streams, heal_b200.graph.FrameInterleaver); 1 = strictly one frame after the other (the number reported as `latency`)")
-    ap.add_argument("--pipeline-depth", type=int, default=3, help="e2e: captured frames in flight in FramePipeline (results are delivered depth-1 submits later)")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="e2e: captured frames in flight in FramePipeline (results are delivered depth-1 submits later)")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one stream, H2D -> frame -> D2H back to back (no copy/compute overlap)")
     opt = ap.parse_args()
     ref = opt.impl == "reference"
