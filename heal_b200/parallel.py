@@ -17,9 +17,15 @@ import torch.distributed as dist
 
 
 def agent_plan(n_agents: int, world: int) -> List[List[int]]:
-    """Contiguous, balanced assignment of agents to ranks; every rank gets ceil(n/world) slots (some may be empty)."""
-    per = -(-n_agents // world)
-    return [[a for a in range(r * per, min((r + 1) * per, n_agents))] for r in range(world)]
+    """Contiguous, balanced assignment of agents to ranks: the first n % world ranks hold ceil(n/world) agents, the others
+    floor(n/world) (5 agents on 4 ranks = 2+1+1+1); every rank's chunk of the gather buffer has ceil(n/world) slots."""
+    base, extra = divmod(n_agents, world)
+    plan, a = [], 0
+    for r in range(world):
+        k = base + (1 if r < extra else 0)
+        plan.append(list(range(a, a + k)))
+        a += k
+    return plan
 
 
 def message_layout(level_shapes: Sequence[Tuple[int, int, int, int]], occ_shapes: Sequence[Tuple[int, int]], elem_bytes: int = 2):

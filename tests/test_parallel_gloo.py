@@ -14,6 +14,7 @@ def test_agent_plan_and_layout():
     assert parallel.agent_plan(5, 2) == [[0, 1, 2], [3, 4]]
     assert parallel.agent_plan(8, 8) == [[i] for i in range(8)]
     assert parallel.agent_plan(5, 8) == [[0], [1], [2], [3], [4], [], [], []]
+    assert parallel.agent_plan(5, 4) == [[0, 1], [2], [3], [4]] and parallel.agent_plan(7, 3) == [[0, 1, 2], [3, 4], [5, 6]]
     offs, total = parallel.message_layout([(2, 256, 256, 64), (2, 128, 128, 128), (2, 64, 64, 256)], [(256, 256), (128, 128), (64, 64)])
     assert total == 7426048 * 4 and offs[0] == 0 and offs[3] == (64 * 256 * 256 + 128 * 128 * 128 + 256 * 64 * 64) * 4
 
