@@ -556,11 +556,11 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // HEAL_TC_* measurement hooks (profiles/tc_experiment.py), read once per process instead of six getenv calls per launch.
 struct TcEnv {
-    int dbg, pdl, halo, bo, tma_store, res_tma, ring;
+    int dbg, pdl, halo, bo, tma_store, res_tma, ring, deep;
     TcEnv() {
         auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
         dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 1); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
-        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1);
+        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1); deep = geti("HEAL_TC_DEEP", 0);
     }
 };
 const TcEnv& tc_env() { static const TcEnv e; return e; }
@@ -781,6 +781,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         default:
             if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, tmR, p, st);
             if (res_tma_ok) return launch_tc<128, 2, 3>(tmA, tmB, tmO, tmR, p, st);
-            return kblocks <= 4 ? launch_tc<128, 2, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, tmR, p, st);
+            // HEAL_TC_DEEP=1 (experiment): 3 stages + 1 staging buffer also for the short-K layers
+            return (kblocks <= 4 && !env.deep) ? launch_tc<128, 2, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, tmR, p, st);
     }
 }
