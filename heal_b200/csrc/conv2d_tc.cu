@@ -782,6 +782,6 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             if (!p.tma_out) return launch_tc<128, 3, 0>(tmA, tmB, tmO, tmR, p, st);
             if (res_tma_ok) return launch_tc<128, 2, 3>(tmA, tmB, tmO, tmR, p, st);
             // HEAL_TC_DEEP=1 (experiment): 3 stages + 1 staging buffer also for the short-K layers
-            return (kblocks <= 4 && !env.deep) ? launch_tc<128, 2, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, tmR, p, st);
+            return (kblocks <= 4 && env.deep != 1) ? launch_tc<128, 2, 2>(tmA, tmB, tmO, tmR, p, st) : launch_tc<128, 3, 1>(tmA, tmB, tmO, tmR, p, st);
     }
 }
