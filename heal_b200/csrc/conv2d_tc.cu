@@ -556,11 +556,11 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // HEAL_TC_* measurement hooks (profiles/tc_experiment.py), read once per process instead of six getenv calls per launch.
 struct TcEnv {
-    int dbg, pdl, halo, bo, tma_store, res_tma, ring, deep;
+    int dbg, pdl, halo, bo, tma_store, res_tma, ring, deep, l2promo;
     TcEnv() {
         auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
         dbg = geti("HEAL_TC_DBG", 0); pdl = geti("HEAL_TC_PDL", 1); halo = geti("HEAL_TC_HALO", 1); bo = geti("HEAL_TC_BO", 0);
-        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1); deep = geti("HEAL_TC_DEEP", 0);
+        tma_store = geti("HEAL_TC_TMA_STORE", 1); res_tma = geti("HEAL_TC_RES_TMA", 1); ring = geti("HEAL_TC_RING", 1); deep = geti("HEAL_TC_DEEP", 0); l2promo = geti("HEAL_TC_L2PROMO", 128);
     }
 };
 const TcEnv& tc_env() { static const TcEnv e; return e; }
@@ -643,6 +643,8 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         p.bo_mode = env.bo;
         p.halo = (want && kh == 3 && kw == 3 && stride == 1 && pad == 1 && p.TH == 1 && block_n == 64 && upsample == 1) ? 1 : 0;
     }
+    // L2 promotion of the activation / residual loads (HEAL_TC_L2PROMO=256: experiment)
+    const CUtensorMapL2promotion act_promo = env.l2promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)planes};
@@ -654,7 +656,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
         void* base = (void*)((const __nv_bfloat16*)in_split + in_coffset);
         if (planes == 1) { strides[3] = strides[2] * N; }
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_128B, act_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
     }
     {
@@ -724,7 +726,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             cuuint32_t es[5] = {1, 1, 1, 1, 1};
             void* base = (void*)((__nv_bfloat16*)out_split + out_coffset);
             CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_SWIZZLE_128B, act_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
             p.tma_out = out_f32 ? 0 : 1;
         }
@@ -743,7 +745,7 @@ extern "C" int heal_conv2d_tc(const void* in_split, size_t in_plane_stride, int 
             cuuint32_t es[5] = {1, 1, 1, 1, 1};
             void* base = (void*)((const __nv_bfloat16*)res_split + res_coffset);
             CUresult r = enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_SWIZZLE_128B, act_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return HEAL_ERR_DRIVER;
             res_tma_ok = true;
             p.res_tma = 1;
