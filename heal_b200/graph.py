@@ -152,7 +152,7 @@ class FramePipeline:
                  compute_streams: int = 2, depth: int = 2):
         """`depth` = captured frames (slots) in flight: `submit` of frame i returns the predictions of frame i - (depth - 1).
         depth 2 keeps one frame queued behind the running one; deeper pipelines keep both compute streams fed while the host
-        waits for a result (measured on C2: depth 2 -> 4 = 305 -> 312 frames/s, results delivered two submits later)."""
+        waits for a result (on C2 depths 2-4 measure the same within run-to-run noise, 290-305 frames/s end to end)."""
         dev = device or next(model.parameters()).device
         self.dev, self.depth = dev, max(2, int(depth))
         self.graphs = [FrameGraph(model, n_agents, point_capacity, pairwise_shape, modality, device=dev) for _ in range(self.depth)]
