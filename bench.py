@@ -814,6 +814,8 @@ def run_gpu(opt):
                         "tensor_pipe_tflops": ach * mma_per_flop if ach else None,
                         "tensor_pipe_frac": ach * mma_per_flop / peak_tf if ach else None,
                         "ms_per_frame": ms, "share_of_step": ms / (serial_ms / opt.steps),
+                        "share_of_instrumented_frame": ms / max(sum(v["ms_per_frame"] for v in kernels.values()), 1e-9),
+                        "share_under_ncu": tj.get("k_conv2d_tc_share_of_frame_under_ncu") if tc else None,
                         "achieved_over_whole_graph_step": (gf / 1e3) / (serial_ms / opt.steps / 1e3),
                         "share_note": "the per-family times come from an EAGER instrumented pass (events around every C-ABI call; the GPU is parked "
                                       "on a spin kernel while the host enqueues the frame, so the intervals hold device time only) and are upper "
